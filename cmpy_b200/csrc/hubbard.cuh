@@ -1,0 +1,339 @@
+// hubbard.cuh -- K4: matrix-free fp64 H.v for Hubbard / Anderson sectors.
+//
+// Amplitudes are a (num_up x num_dn) row-major matrix X (idx = up_idx*num_dn + dn_idx,
+// ref: cmpy/operators.py:33-90).  H.X = D o X + X T_dn^T + T_up X:
+//   D      diagonal  E_up[u] + E_dn[d] + sum_i u_i [up&dn]_i   (ref: operators.py:305-422)
+//   T_dn   dn hops: gathers inside one row                     (ref: operators.py:522-527)
+//   T_up   up hops: whole-row gathers from other rows          (ref: operators.py:515-520)
+// Matrix element of a hop = sign*hop (ref: operators.py:425-460).
+//
+// Kernels:
+//   hub_flat_kernel  one thread per amplitude, every source read from global (L1/L2);
+//                    any sector shape (num_dn may be 1).
+//   hub_row_kernel   persistent CTAs, one row at a time: the row of x is staged in shared
+//                    memory (all dn-hop gathers hit smem), up-hop sources are coalesced
+//                    reads of whole remote rows.
+// Both optionally fuse the Lanczos step  w = Hx/beta_j - (beta_j/beta_{j-1}) w_old,
+// alpha_j = <x/beta_j, w>  (ref recurrence: cmpy/exactdiag.py:324-347).
+#pragma once
+#include "common.cuh"
+#include "sector.cuh"
+
+struct HubParams {
+  i64 num_up, num_dn;
+  const uint32_t* up_states;  // 32-bit copies of the strings
+  const uint32_t* dn_states;
+  const uint32_t* ell_up; const uint8_t* cnt_up;
+  const uint32_t* ell_dn; const uint8_t* cnt_dn;
+  const double* e_up; const double* e_dn;
+  const double* hop;  // [nbonds]
+  const double* u;    // [num_sites]
+  int num_sites;
+  double u0, hop0;
+  i64 row0, nrows;    // slab of rows handled by this launch (x, y point at the slab)
+  int with_up;        // include up hops (needs the whole vector: row0 == 0, nrows == num_up)
+  int accumulate;     // y += instead of y =
+  const double* x;
+  double* y;
+  LzCtx lz;
+};
+
+template <bool UNI>
+__device__ __forceinline__ double hub_diag(const HubParams& p, uint32_t ups, uint32_t dns,
+                                           double eu, double ed) {
+  if (UNI) return eu + ed + p.u0 * (double)__popc(ups & dns);
+  uint32_t both = ups & dns;
+  double w = 0.0;
+  while (both) {
+    int i = __ffs(both) - 1;
+    both &= both - 1;
+    w += p.u[i];
+  }
+  return eu + ed + w;
+}
+
+template <bool LZ>
+__device__ __forceinline__ void hub_store(const HubParams& p, i64 i, double acc, double xi,
+                                          double s1, double s2, bool has_prev, double& dot) {
+  if (LZ) {
+    double w = s1 * acc;
+    if (has_prev) w -= s2 * p.y[i];
+    p.y[i] = w;
+    dot += (s1 * xi) * w;
+  } else {
+    p.y[i] = p.accumulate ? p.y[i] + acc : acc;
+  }
+}
+
+template <bool LZ>
+__device__ __forceinline__ void lz_scalars(const LzCtx& lz, int& j, double& s1, double& s2,
+                                           bool& has_prev) {
+  j = 0; s1 = 1.0; s2 = 0.0; has_prev = false;
+  if (LZ) {
+    j = *lz.iter;
+    double bj = lz.beta[j];
+    s1 = 1.0 / bj;
+    has_prev = j > 0;
+    if (has_prev) s2 = bj / lz.beta[j - 1];
+  }
+}
+
+template <bool LZ>
+__device__ __forceinline__ void lz_finish(const LzCtx& lz, int j, double dot, double* red) {
+  if (LZ) {
+    double bsum = block_sum(dot, red);
+    double total;
+    if (grid_sum_last(bsum, lz.partials, lz.ticket, red, &total)) lz.alpha[j] = total;
+  }
+}
+
+template <bool UNI, bool LZ>
+__global__ void __launch_bounds__(256) hub_flat_kernel(HubParams p) {
+  __shared__ double red[32];
+  int j; double s1, s2; bool has_prev;
+  lz_scalars<LZ>(p.lz, j, s1, s2, has_prev);
+  const i64 nd = p.num_dn, nu = p.num_up;
+  const i64 total = p.nrows * nd;
+  double dot = 0.0;
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total;
+       i += (i64)gridDim.x * blockDim.x) {
+    const i64 r = i / nd, d = i - r * nd, u = p.row0 + r;
+    const uint32_t ups = p.up_states[u], dns = p.dn_states[d];
+    const double xi = p.x[i];
+    double acc = hub_diag<UNI>(p, ups, dns, p.e_up[u], p.e_dn[d]) * xi;
+    double h = 0.0;
+    const double* xr = p.x + r * nd;
+    int c = p.cnt_dn[d];
+    for (int k = 0; k < c; ++k) {
+      uint32_t e = p.ell_dn[(i64)k * nd + d];
+      double v = xr[e & ELL_TGT_MASK];
+      if (UNI) h += (e >> 31) ? -v : v;
+      else acc += ((e >> 31) ? -v : v) * p.hop[(e >> ELL_TGT_BITS) & 63u];
+    }
+    if (p.with_up) {
+      c = p.cnt_up[u];
+      for (int k = 0; k < c; ++k) {
+        uint32_t e = p.ell_up[(i64)k * nu + u];
+        double v = p.x[(i64)(e & ELL_TGT_MASK) * nd + d];
+        if (UNI) h += (e >> 31) ? -v : v;
+        else acc += ((e >> 31) ? -v : v) * p.hop[(e >> ELL_TGT_BITS) & 63u];
+      }
+    }
+    if (UNI) acc += p.hop0 * h;
+    hub_store<LZ>(p, i, acc, xi, s1, s2, has_prev, dot);
+  }
+  lz_finish<LZ>(p.lz, j, dot, red);
+}
+
+// Row kernel: dynamic smem = num_dn doubles (the staged row).
+template <bool UNI, bool LZ>
+__global__ void hub_row_kernel(HubParams p) {
+  extern __shared__ __align__(16) double xs[];
+  __shared__ double red[32];
+  __shared__ uint32_t s_up[ELL_MAX_BONDS];
+  int j; double s1, s2; bool has_prev;
+  lz_scalars<LZ>(p.lz, j, s1, s2, has_prev);
+  const i64 nd = p.num_dn, nu = p.num_up;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double dot = 0.0;
+  for (i64 r = blockIdx.x; r < p.nrows; r += gridDim.x) {
+    const i64 u = p.row0 + r;
+    const double* __restrict__ xr = p.x + r * nd;
+    // stage the row
+    for (i64 d = tid; d < nd; d += nt) xs[d] = xr[d];
+    const int cu = p.with_up ? (int)p.cnt_up[u] : 0;
+    if (tid < cu) s_up[tid] = p.ell_up[(i64)tid * nu + u];
+    __syncthreads();
+    const uint32_t ups = p.up_states[u];
+    const double eu = p.e_up[u];
+    for (i64 d = tid; d < nd; d += nt) {
+      const uint32_t dns = p.dn_states[d];
+      const double xi = xs[d];
+      double acc = hub_diag<UNI>(p, ups, dns, eu, p.e_dn[d]) * xi;
+      double h = 0.0;
+      const int c = p.cnt_dn[d];
+      for (int k = 0; k < c; ++k) {
+        uint32_t e = p.ell_dn[(i64)k * nd + d];
+        double v = xs[e & ELL_TGT_MASK];
+        if (UNI) h += (e >> 31) ? -v : v;
+        else acc += ((e >> 31) ? -v : v) * p.hop[(e >> ELL_TGT_BITS) & 63u];
+      }
+      for (int k = 0; k < cu; ++k) {
+        uint32_t e = s_up[k];
+        double v = p.x[(i64)(e & ELL_TGT_MASK) * nd + d];
+        if (UNI) h += (e >> 31) ? -v : v;
+        else acc += ((e >> 31) ? -v : v) * p.hop[(e >> ELL_TGT_BITS) & 63u];
+      }
+      if (UNI) acc += p.hop0 * h;
+      hub_store<LZ>(p, r * nd + d, acc, xi, s1, s2, has_prev, dot);
+    }
+    __syncthreads();
+  }
+  lz_finish<LZ>(p.lz, j, dot, red);
+}
+
+template <bool UNI>
+__global__ void hub_diag_kernel(HubParams p, double* __restrict__ diag) {
+  const i64 nd = p.num_dn;
+  const i64 total = p.num_up * nd;
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total;
+       i += (i64)gridDim.x * blockDim.x) {
+    const i64 u = i / nd, d = i - u * nd;
+    diag[i] = hub_diag<UNI>(p, p.up_states[u], p.dn_states[d], p.e_up[u], p.e_dn[d]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+struct SpeciesTables {
+  i64 num = 0;
+  int width = 0;
+  i64* d_states = nullptr;
+  uint32_t* d_states32 = nullptr;
+  uint32_t* d_ell = nullptr;
+  uint8_t* d_cnt = nullptr;
+  double* d_energy = nullptr;
+  void release() {
+    cudaFree(d_states); cudaFree(d_states32); cudaFree(d_ell); cudaFree(d_cnt); cudaFree(d_energy);
+    d_states = nullptr; d_states32 = nullptr; d_ell = nullptr; d_cnt = nullptr; d_energy = nullptr;
+  }
+};
+
+__global__ void narrow_states_kernel(const i64* __restrict__ in, i64 n, uint32_t* __restrict__ out) {
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    out[i] = (uint32_t)in[i];
+}
+
+struct HubbardOp : cmpy_op_s {
+  int num_sites = 0, nbonds = 0, sign_width = 0;
+  SpeciesTables up, dn;
+  double* d_hop = nullptr;
+  double* d_u = nullptr;
+  bool uniform = false;
+  double u0 = 0.0, hop0 = 0.0;
+  int row_threads = 256;
+  int row_blocks_per_sm = 1;
+  bool row_ok = false;
+
+  ~HubbardOp() override {
+    up.release(); dn.release();
+    cudaFree(d_hop); cudaFree(d_u);
+  }
+
+  HubParams base_params() const {
+    HubParams p;
+    p.num_up = up.num; p.num_dn = dn.num;
+    p.up_states = up.d_states32; p.dn_states = dn.d_states32;
+    p.ell_up = up.d_ell; p.cnt_up = up.d_cnt;
+    p.ell_dn = dn.d_ell; p.cnt_dn = dn.d_cnt;
+    p.e_up = up.d_energy; p.e_dn = dn.d_energy;
+    p.hop = d_hop; p.u = d_u; p.num_sites = num_sites;
+    p.u0 = u0; p.hop0 = hop0;
+    p.row0 = 0; p.nrows = up.num; p.with_up = 1; p.accumulate = 0;
+    p.x = nullptr; p.y = nullptr;
+    p.lz.enabled = 0; p.lz.iter = nullptr; p.lz.beta = nullptr; p.lz.alpha = nullptr;
+    p.lz.partials = d_partials; p.lz.ticket = d_ticket;
+    return p;
+  }
+
+  int build_species(SpeciesTables& t, const i64* h_states, i64 num, int fixed_popcount,
+                    const BondList& bl, const SiteValues& eps) {
+    t.num = num;
+    ARG_CHECK(num >= 1, "empty string list");
+    ARG_CHECK(num <= (i64)ELL_TGT_MASK, "string list too long for the packed hop table");
+    CU_CHECK(cudaMalloc(&t.d_states, sizeof(i64) * num));
+    CU_CHECK(cudaMemcpy(t.d_states, h_states, sizeof(i64) * num, cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMalloc(&t.d_states32, sizeof(uint32_t) * num));
+    CU_CHECK(cudaMalloc(&t.d_cnt, num));
+    CU_CHECK(cudaMalloc(&t.d_energy, sizeof(double) * num));
+    narrow_states_kernel<<<grid_for(num, 256), 256>>>(t.d_states, num, t.d_states32);
+    KERNEL_CHECK();
+    weighted_elements_kernel<<<grid_for(num, 256), 256>>>(t.d_states, num, eps, t.d_energy);
+    KERNEL_CHECK();
+    // pass 1: counts only (ell_width = 0), then size the ELL table to the max count
+    species_ell_kernel<<<grid_for(num, 128), 128>>>(t.d_states, num, fixed_popcount, sign_width,
+                                                    bl, 0, nullptr, t.d_cnt);
+    KERNEL_CHECK();
+    std::vector<uint8_t> h_cnt(num);
+    CU_CHECK(cudaMemcpy(h_cnt.data(), t.d_cnt, num, cudaMemcpyDeviceToHost));
+    int w = 0;
+    for (i64 i = 0; i < num; ++i) w = h_cnt[i] > w ? h_cnt[i] : w;
+    t.width = w;
+    CU_CHECK(cudaMalloc(&t.d_ell, sizeof(uint32_t) * (size_t)(w > 0 ? w : 1) * num));
+    if (w > 0) {
+      species_ell_kernel<<<grid_for(num, 128), 128>>>(t.d_states, num, fixed_popcount,
+                                                      sign_width, bl, w, t.d_ell, t.d_cnt);
+      KERNEL_CHECK();
+    }
+    CU_CHECK(cudaDeviceSynchronize());
+    return CMPY_OK;
+  }
+
+  template <bool UNI, bool LZ>
+  int launch(HubParams& p, int use_variant, cudaStream_t st) {
+    const i64 total = p.nrows * p.num_dn;
+    if (total == 0) return CMPY_OK;
+    bool use_row = (use_variant == 2) || (use_variant == 0 && row_ok);
+    if (use_variant == 2 && !row_ok)
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row variant: the dn row does not fit shared memory");
+    if (use_row) {
+      size_t smem = sizeof(double) * (size_t)p.num_dn;
+      i64 g = (i64)sm_count * row_blocks_per_sm;
+      if (g > p.nrows) g = p.nrows;
+      if (LZ && g > max_blocks) g = max_blocks;
+      hub_row_kernel<UNI, LZ><<<(int)g, row_threads, smem, st>>>(p);
+    } else {
+      int g = grid_for(total, 256, sm_count * 8);
+      hub_flat_kernel<UNI, LZ><<<g, 256, 0, st>>>(p);
+    }
+    KERNEL_CHECK();
+    return CMPY_OK;
+  }
+
+  template <bool UNI>
+  int configure_row() {
+    size_t smem = sizeof(double) * (size_t)dn.num;
+    row_ok = false;
+    if (dn.num < 64 || (i64)smem > smem_optin - 2048) return CMPY_OK;
+    i64 t = (dn.num + 3) / 4;
+    t = ((t + 31) / 32) * 32;
+    if (t < 64) t = 64;
+    if (t > 512) t = 512;
+    row_threads = (int)t;
+    CU_CHECK(cudaFuncSetAttribute(hub_row_kernel<UNI, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CHECK(cudaFuncSetAttribute(hub_row_kernel<UNI, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_row_kernel<UNI, true>,
+                                                           row_threads, smem));
+    if (nb < 1) return CMPY_OK;
+    row_blocks_per_sm = nb > 8 ? 8 : nb;
+    row_ok = true;
+    return CMPY_OK;
+  }
+
+  int apply_slab(const double* x, double* y, i64 row0, i64 nrows, int with_up, int accumulate,
+                 const LzCtx& lz, cudaStream_t st) {
+    HubParams p = base_params();
+    p.x = x; p.y = y; p.row0 = row0; p.nrows = nrows; p.with_up = with_up;
+    p.accumulate = accumulate;
+    if (lz.enabled) {
+      p.lz = lz; p.lz.partials = d_partials; p.lz.ticket = d_ticket;
+      return uniform ? launch<true, true>(p, variant, st) : launch<false, true>(p, variant, st);
+    }
+    return uniform ? launch<true, false>(p, variant, st) : launch<false, false>(p, variant, st);
+  }
+
+  int apply(const double* x, double* y, const LzCtx& lz, cudaStream_t st) override {
+    return apply_slab(x, y, 0, up.num, 1, 0, lz, st);
+  }
+
+  int diagonal(double* d_diag, cudaStream_t st) override {
+    HubParams p = base_params();
+    int g = grid_for(size, 256, sm_count * 8);
+    if (uniform) hub_diag_kernel<true><<<g, 256, 0, st>>>(p, d_diag);
+    else hub_diag_kernel<false><<<g, 256, 0, st>>>(p, d_diag);
+    KERNEL_CHECK();
+    return CMPY_OK;
+  }
+};

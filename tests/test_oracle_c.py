@@ -1,0 +1,38 @@
+"""Pins the C oracle (oracle/hv_oracle.c) to the numpy oracle and the reference fixtures."""
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+import oracle_np as orc
+import oracle_c as orcc
+
+
+def test_c_enumerate():
+    for L, n in [(4, 2), (9, 4), (12, 6), (16, 8), (5, 0), (5, 5)]:
+        assert_array_equal(orcc.enumerate_states(L, n), orc.enumerate_states(L, n))
+
+
+def test_c_hv_golden(golden):
+    o = orcc.hubbard_oracle(8, 4, 4, orc.chain_neighbors(8), 4.0, -2.0, 1.0)
+    x = np.cos(0.37 * np.arange(4900))
+    ref = golden["hub_chain8_44_hv"]
+    assert np.abs(o.matvec(x) - ref).max() / np.abs(ref).max() < 1e-13
+    assert_array_equal(o.matvec_rows(x, 10, 5, nthreads=1), o.matvec(x)[700:1050])
+
+
+@pytest.mark.parametrize("L,nu,nd,nb", [(6, 3, 3, orc.chain_neighbors(6, True)), (9, 4, 5, orc.square_neighbors(3, 3)),
+                                       (10, 5, 5, orc.chain_neighbors(10))])
+def test_c_hv_vs_numpy(L, nu, nd, nb):
+    o = orcc.hubbard_oracle(L, nu, nd, nb, 3.0, -0.7, 0.9)
+    x = np.random.default_rng(0).standard_normal(o.size)
+    ref = orc.hubbard_matvec_free(o.up, o.dn, nb, 3.0, -0.7, 0.9, x, width=L)
+    assert np.abs(o.matvec(x) - ref).max() / np.abs(ref).max() < 1e-13
+
+
+def test_c_siam_signless(golden):
+    up = dn = orc.enumerate_states(4, 2)
+    o = orcc.HubbardOracle(4, up, dn, [(0, 1), (0, 2), (0, 3)], [1.0, 0.7, 0.4],
+                           [0.0 - 1.0, 0.1, 0.2, 0.3], [2.0, 0, 0, 0], 0)
+    x = np.cos(0.37 * np.arange(36))
+    ref = golden["siam4_22_hv"]
+    assert np.abs(o.matvec(x) - ref).max() < 1e-13
