@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "sector.cuh"
 #include "hubbard.cuh"
+#include "hubbard_seg.cuh"
+#include "hubbard_op.cuh"
 #include "lanczos.cuh"
 #include "greens.cuh"
 #include "heisenberg.cuh"
@@ -146,13 +148,16 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
   rc = op->build_species(op->up, (const i64*)h_up_states, num_up, fixed_popcount, bl, eps);
   if (!rc) rc = op->build_species(op->dn, (const i64*)h_dn_states, num_dn, fixed_popcount, bl, eps);
   if (rc) { delete op; return rc; }
-  bool uni = true;
+  bool uni = true, eps_uni = true;
+  for (int i = 1; i < num_sites; ++i) eps_uni = eps_uni && (h_eps[i] == h_eps[0]);
+  op->eps_uniform = eps_uni;
   for (int i = 1; i < num_sites; ++i) uni = uni && (h_u[i] == h_u[0]);
   for (int b = 1; b < nbonds; ++b) uni = uni && (h_hop[b] == h_hop[0]);
   op->uniform = uni;
   op->u0 = h_u[0];
   op->hop0 = nbonds > 0 ? h_hop[0] : 0.0;
-  cudaError_t e = cudaMalloc(&op->d_hop, sizeof(double) * (nbonds > 0 ? nbonds : 1));
+  cudaError_t e = cudaMalloc(&op->d_hop, sizeof(double) * ELL_MAX_BONDS);  // zero padded
+  if (e == cudaSuccess) e = cudaMemset(op->d_hop, 0, sizeof(double) * ELL_MAX_BONDS);
   if (e == cudaSuccess) e = cudaMalloc(&op->d_u, sizeof(double) * num_sites);
   if (e == cudaSuccess && nbonds > 0)
     e = cudaMemcpy(op->d_hop, h_hop, sizeof(double) * nbonds, cudaMemcpyHostToDevice);
@@ -162,6 +167,8 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
     return cmpy_fail(CMPY_ERR_CUDA, std::string("hubbard_create: ") + cudaGetErrorString(e));
   }
   rc = uni ? op->configure_row<true>() : op->configure_row<false>();
+  if (!rc && fixed_popcount)
+    rc = op->configure_seg(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (rc) { delete op; return rc; }
   *out = op;
   return CMPY_OK;
@@ -246,7 +253,7 @@ API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_
 }
 
 API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
-  ARG_CHECK(op && variant >= 0 && variant <= 2, "bad variant");
+  ARG_CHECK(op && variant >= 0 && variant <= 3, "bad variant");
   op->variant = variant;
   return CMPY_OK;
 }

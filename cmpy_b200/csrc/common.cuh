@@ -168,6 +168,17 @@ __device__ __forceinline__ bool grid_sum_last(double block_partial, double* part
   return threadIdx.x == 0;
 }
 
+// Raise a kernel's dynamic shared memory limit to the device maximum (idempotent; never
+// lowers it, so operators of different sizes can coexist).
+template <typename K>
+static int raise_smem_limit(K kernel, i64 optin) {
+  cudaFuncAttributes a;
+  CU_CHECK(cudaFuncGetAttributes(&a, kernel));
+  const int maxdyn = (int)(optin - (i64)a.sharedSizeBytes);
+  CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+  return CMPY_OK;
+}
+
 // Lanczos fusion context (device scalars live in one small buffer owned by the handle)
 struct LzCtx {
   int enabled;        // 0: plain y = Hx

@@ -259,8 +259,9 @@ struct HeisenbergOp : cmpy_op_s {
     i64 t = ((max_len + 3) / 4 + 31) / 32 * 32;
     if (t < 64) t = 64; if (t > 512) t = 512;
     threads = (int)t;
-    CU_CHECK(cudaFuncSetAttribute(heis_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_CHECK(cudaFuncSetAttribute(heis_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rcs = raise_smem_limit(heis_row_kernel<false>, smem_optin);
+    if (!rcs) rcs = raise_smem_limit(heis_row_kernel<true>, smem_optin);
+    if (rcs) return rcs;
     int nb = 0;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, heis_row_kernel<true>, threads, smem));
     ARG_CHECK(nb >= 1, "heisenberg: row does not fit shared memory");

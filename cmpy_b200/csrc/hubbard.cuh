@@ -183,157 +183,3 @@ __global__ void hub_diag_kernel(HubParams p, double* __restrict__ diag) {
   }
 }
 
-// ---------------------------------------------------------------------------------
-struct SpeciesTables {
-  i64 num = 0;
-  int width = 0;
-  i64* d_states = nullptr;
-  uint32_t* d_states32 = nullptr;
-  uint32_t* d_ell = nullptr;
-  uint8_t* d_cnt = nullptr;
-  double* d_energy = nullptr;
-  void release() {
-    cudaFree(d_states); cudaFree(d_states32); cudaFree(d_ell); cudaFree(d_cnt); cudaFree(d_energy);
-    d_states = nullptr; d_states32 = nullptr; d_ell = nullptr; d_cnt = nullptr; d_energy = nullptr;
-  }
-};
-
-__global__ void narrow_states_kernel(const i64* __restrict__ in, i64 n, uint32_t* __restrict__ out) {
-  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-    out[i] = (uint32_t)in[i];
-}
-
-struct HubbardOp : cmpy_op_s {
-  int num_sites = 0, nbonds = 0, sign_width = 0;
-  SpeciesTables up, dn;
-  double* d_hop = nullptr;
-  double* d_u = nullptr;
-  bool uniform = false;
-  double u0 = 0.0, hop0 = 0.0;
-  int row_threads = 256;
-  int row_blocks_per_sm = 1;
-  bool row_ok = false;
-
-  ~HubbardOp() override {
-    up.release(); dn.release();
-    cudaFree(d_hop); cudaFree(d_u);
-  }
-
-  HubParams base_params() const {
-    HubParams p;
-    p.num_up = up.num; p.num_dn = dn.num;
-    p.up_states = up.d_states32; p.dn_states = dn.d_states32;
-    p.ell_up = up.d_ell; p.cnt_up = up.d_cnt;
-    p.ell_dn = dn.d_ell; p.cnt_dn = dn.d_cnt;
-    p.e_up = up.d_energy; p.e_dn = dn.d_energy;
-    p.hop = d_hop; p.u = d_u; p.num_sites = num_sites;
-    p.u0 = u0; p.hop0 = hop0;
-    p.row0 = 0; p.nrows = up.num; p.with_up = 1; p.accumulate = 0;
-    p.x = nullptr; p.y = nullptr;
-    p.lz.enabled = 0; p.lz.iter = nullptr; p.lz.beta = nullptr; p.lz.alpha = nullptr;
-    p.lz.partials = d_partials; p.lz.ticket = d_ticket;
-    return p;
-  }
-
-  int build_species(SpeciesTables& t, const i64* h_states, i64 num, int fixed_popcount,
-                    const BondList& bl, const SiteValues& eps) {
-    t.num = num;
-    ARG_CHECK(num >= 1, "empty string list");
-    ARG_CHECK(num <= (i64)ELL_TGT_MASK, "string list too long for the packed hop table");
-    CU_CHECK(cudaMalloc(&t.d_states, sizeof(i64) * num));
-    CU_CHECK(cudaMemcpy(t.d_states, h_states, sizeof(i64) * num, cudaMemcpyHostToDevice));
-    CU_CHECK(cudaMalloc(&t.d_states32, sizeof(uint32_t) * num));
-    CU_CHECK(cudaMalloc(&t.d_cnt, num));
-    CU_CHECK(cudaMalloc(&t.d_energy, sizeof(double) * num));
-    narrow_states_kernel<<<grid_for(num, 256), 256>>>(t.d_states, num, t.d_states32);
-    KERNEL_CHECK();
-    weighted_elements_kernel<<<grid_for(num, 256), 256>>>(t.d_states, num, eps, t.d_energy);
-    KERNEL_CHECK();
-    // pass 1: counts only (ell_width = 0), then size the ELL table to the max count
-    species_ell_kernel<<<grid_for(num, 128), 128>>>(t.d_states, num, fixed_popcount, sign_width,
-                                                    bl, 0, nullptr, t.d_cnt);
-    KERNEL_CHECK();
-    std::vector<uint8_t> h_cnt(num);
-    CU_CHECK(cudaMemcpy(h_cnt.data(), t.d_cnt, num, cudaMemcpyDeviceToHost));
-    int w = 0;
-    for (i64 i = 0; i < num; ++i) w = h_cnt[i] > w ? h_cnt[i] : w;
-    t.width = w;
-    CU_CHECK(cudaMalloc(&t.d_ell, sizeof(uint32_t) * (size_t)(w > 0 ? w : 1) * num));
-    if (w > 0) {
-      species_ell_kernel<<<grid_for(num, 128), 128>>>(t.d_states, num, fixed_popcount,
-                                                      sign_width, bl, w, t.d_ell, t.d_cnt);
-      KERNEL_CHECK();
-    }
-    CU_CHECK(cudaDeviceSynchronize());
-    return CMPY_OK;
-  }
-
-  template <bool UNI, bool LZ>
-  int launch(HubParams& p, int use_variant, cudaStream_t st) {
-    const i64 total = p.nrows * p.num_dn;
-    if (total == 0) return CMPY_OK;
-    bool use_row = (use_variant == 2) || (use_variant == 0 && row_ok);
-    if (use_variant == 2 && !row_ok)
-      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row variant: the dn row does not fit shared memory");
-    if (use_row) {
-      size_t smem = sizeof(double) * (size_t)p.num_dn;
-      i64 g = (i64)sm_count * row_blocks_per_sm;
-      if (g > p.nrows) g = p.nrows;
-      if (LZ && g > max_blocks) g = max_blocks;
-      hub_row_kernel<UNI, LZ><<<(int)g, row_threads, smem, st>>>(p);
-    } else {
-      int g = grid_for(total, 256, sm_count * 8);
-      hub_flat_kernel<UNI, LZ><<<g, 256, 0, st>>>(p);
-    }
-    KERNEL_CHECK();
-    return CMPY_OK;
-  }
-
-  template <bool UNI>
-  int configure_row() {
-    size_t smem = sizeof(double) * (size_t)dn.num;
-    row_ok = false;
-    if (dn.num < 64 || (i64)smem > smem_optin - 2048) return CMPY_OK;
-    i64 t = (dn.num + 3) / 4;
-    t = ((t + 31) / 32) * 32;
-    if (t < 64) t = 64;
-    if (t > 512) t = 512;
-    row_threads = (int)t;
-    CU_CHECK(cudaFuncSetAttribute(hub_row_kernel<UNI, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_CHECK(cudaFuncSetAttribute(hub_row_kernel<UNI, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_row_kernel<UNI, true>,
-                                                           row_threads, smem));
-    if (nb < 1) return CMPY_OK;
-    row_blocks_per_sm = nb > 8 ? 8 : nb;
-    row_ok = true;
-    return CMPY_OK;
-  }
-
-  int apply_slab(const double* x, double* y, i64 row0, i64 nrows, int with_up, int accumulate,
-                 const LzCtx& lz, cudaStream_t st) {
-    HubParams p = base_params();
-    p.x = x; p.y = y; p.row0 = row0; p.nrows = nrows; p.with_up = with_up;
-    p.accumulate = accumulate;
-    if (lz.enabled) {
-      p.lz = lz; p.lz.partials = d_partials; p.lz.ticket = d_ticket;
-      return uniform ? launch<true, true>(p, variant, st) : launch<false, true>(p, variant, st);
-    }
-    return uniform ? launch<true, false>(p, variant, st) : launch<false, false>(p, variant, st);
-  }
-
-  int apply(const double* x, double* y, const LzCtx& lz, cudaStream_t st) override {
-    return apply_slab(x, y, 0, up.num, 1, 0, lz, st);
-  }
-
-  int diagonal(double* d_diag, cudaStream_t st) override {
-    HubParams p = base_params();
-    int g = grid_for(size, 256, sm_count * 8);
-    if (uniform) hub_diag_kernel<true><<<g, 256, 0, st>>>(p, d_diag);
-    else hub_diag_kernel<false><<<g, 256, 0, st>>>(p, d_diag);
-    KERNEL_CHECK();
-    return CMPY_OK;
-  }
-};
