@@ -63,7 +63,8 @@ SIGNATURES = {
     "cmpy_cf_eval": (c_int, [POINTER(c_double), POINTER(c_double), c_int, c_double, c_double, c_int,
                              _p, c_int64, _p, c_int, _p]),
     "cmpy_pole_sum": (c_int, [_p, _p, c_int64, _p, c_int64, _p, c_int, _p]),
-    "cmpy_transpose": (c_int, [_p, c_int64, c_int64, c_int64, _p, c_int, _p]),
+    "cmpy_transpose": (c_int, [_p, c_int64, c_int64, c_int64, _p, c_int64, c_int, _p]),
+    "cmpy_copy2d": (c_int, [_p, c_int64, c_int64, c_int64, _p, c_int64, c_int, _p]),
 }
 
 

@@ -253,7 +253,7 @@ API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_
 }
 
 API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
-  ARG_CHECK(op && variant >= 0 && variant <= 3, "bad variant");
+  ARG_CHECK(op && variant >= 0 && variant <= 4, "bad variant");
   op->variant = variant;
   return CMPY_OK;
 }
@@ -376,14 +376,27 @@ API int cmpy_pole_sum(const double* d_weights, const double* d_poles, int64_t np
   return CMPY_OK;
 }
 
-// ---- K9 building block -------------------------------------------------------------
+// ---- K9 building blocks -------------------------------------------------------------
 API int cmpy_transpose(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
-                       double* d_out, int accumulate, void* stream) {
-  ARG_CHECK(d_in && d_out && nrows >= 0 && ncols >= 0 && ld_in >= ncols, "bad argument");
+                       double* d_out, int64_t ld_out, int accumulate, void* stream) {
+  ARG_CHECK(d_in && d_out && nrows >= 0 && ncols >= 0 && ld_in >= ncols && ld_out >= nrows,
+            "bad argument");
   if (nrows == 0 || ncols == 0) return CMPY_OK;
   i64 ntiles = ((nrows + 31) / 32) * ((ncols + 31) / 32);
   int g = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
-  transpose_kernel<<<g, 256, 0, as_stream(stream)>>>(d_in, nrows, ncols, ld_in, d_out, accumulate);
+  transpose_kernel<<<g, 256, 0, as_stream(stream)>>>(d_in, nrows, ncols, ld_in, d_out, ld_out,
+                                                     accumulate);
+  KERNEL_CHECK();
+  return CMPY_OK;
+}
+
+API int cmpy_copy2d(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
+                    double* d_out, int64_t ld_out, int accumulate, void* stream) {
+  ARG_CHECK(d_in && d_out && nrows >= 0 && ncols >= 0 && ld_in >= ncols && ld_out >= ncols,
+            "bad argument");
+  if (nrows == 0 || ncols == 0) return CMPY_OK;
+  copy2d_kernel<<<grid_for(nrows * ncols, 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+      d_in, nrows, ncols, ld_in, d_out, ld_out, accumulate);
   KERNEL_CHECK();
   return CMPY_OK;
 }

@@ -173,11 +173,12 @@ struct CooOp : cmpy_op_s {
   }
 };
 
-// ---- slab transpose --------------------------------------------------------------
-// out[c*nrows + r] (+)= in[r*ld_in + c]; 32x32 tiles through padded shared memory
+// ---- slab transpose / placement ---------------------------------------------------
+// out[c*ld_out + r] (+)= in[r*ld_in + c]; 32x32 tiles through padded shared memory
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, i64 nrows,
                                                        i64 ncols, i64 ld_in,
-                                                       double* __restrict__ out, int accumulate) {
+                                                       double* __restrict__ out, i64 ld_out,
+                                                       int accumulate) {
   __shared__ double tile[32][33];
   const i64 tiles_c = (ncols + 31) / 32, tiles_r = (nrows + 31) / 32;
   const i64 ntiles = tiles_c * tiles_r;
@@ -197,9 +198,23 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
       i64 c = c0 + ty + k, r = r0 + tx;
       if (r < nrows && c < ncols) {
         double v = tile[tx][ty + k];
-        i64 o = c * nrows + r;
+        i64 o = c * ld_out + r;
         out[o] = accumulate ? out[o] + v : v;
       }
     }
+  }
+}
+
+// out[r*ld_out + c] (+)= in[r*ld_in + c]  (pitched block copy / accumulate)
+__global__ void __launch_bounds__(256) copy2d_kernel(const double* __restrict__ in, i64 nrows,
+                                                    i64 ncols, i64 ld_in, double* __restrict__ out,
+                                                    i64 ld_out, int accumulate) {
+  const i64 total = nrows * ncols;
+  for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < total;
+       i += (i64)gridDim.x * blockDim.x) {
+    const i64 r = i / ncols, c = i - r * ncols;
+    const double v = in[r * ld_in + c];
+    const i64 o = r * ld_out + c;
+    out[o] = accumulate ? out[o] + v : v;
   }
 }

@@ -38,6 +38,7 @@ struct HubbardOp : cmpy_op_s {
   SegTables seg;
   int seg_threads = 256;
   int seg_blocks_per_sm = 1;
+  bool seg_wide = false;     // 1024-thread CTAs (one CTA per SM, long rows)
 
   ~HubbardOp() override {
     up.release(); dn.release(); seg.release();
@@ -99,7 +100,16 @@ struct HubbardOp : cmpy_op_s {
     if (total == 0) return CMPY_OK;
     if (use_variant == 3 && !seg.ok)
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "segment variant not available for this sector");
-    if (use_variant == 3 || (use_variant == 0 && seg.ok)) return launch_seg<LZ>(p, st);
+    if (use_variant == 4 && !seg.ok)
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "segment variant not available for this sector");
+    if (use_variant == 3 || use_variant == 4 || (use_variant == 0 && seg.ok)) {
+      const bool saved = seg_wide;
+      if (use_variant == 3) seg_wide = false;
+      if (use_variant == 4) seg_wide = true;
+      int rc = launch_seg<LZ>(p, st);
+      seg_wide = saved;
+      return rc;
+    }
     bool use_row = (use_variant == 2) || (use_variant == 0 && row_ok);
     if (use_variant == 2 && !row_ok)
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row variant: the dn row does not fit shared memory");
@@ -117,35 +127,52 @@ struct HubbardOp : cmpy_op_s {
     return CMPY_OK;
   }
 
+  size_t seg_smem() const {
+    return (size_t)seg.lay.bytes + (((size_t)dn.num * 4 + 15) & ~(size_t)15) + sizeof(double) * (size_t)dn.num;
+  }
+
   template <bool LZ>
   int launch_seg(HubParams& p, cudaStream_t st) {
     SegParams sp;
     sp.hp = p; sp.lay = seg.lay; sp.blob = seg.d_blob; sp.e_dn_const = seg.e_dn_const;
-    const size_t smem = (size_t)seg.lay.bytes + sizeof(double) * (size_t)p.num_dn;
+    const size_t smem = seg_smem();
     i64 g = (i64)sm_count * seg_blocks_per_sm;
     if (g > p.nrows) g = p.nrows;
     const bool uni = uniform && eps_uniform;
-    if (seg.wll_pad == 8) {
-      if (uni) hub_seg_kernel<true, LZ, 8><<<(int)g, seg_threads, smem, st>>>(sp);
-      else hub_seg_kernel<false, LZ, 8><<<(int)g, seg_threads, smem, st>>>(sp);
+    // 16-byte vector path: even row length and 16-byte aligned slab pointers
+    const bool vec = ((dn.num & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+    if (seg_wide) {
+      const int nt = 1024;
+      if (vec) {
+        if (uni) hub_seg_kernel<true, LZ, true, 1024><<<(int)g, nt, smem, st>>>(sp);
+        else hub_seg_kernel<false, LZ, true, 1024><<<(int)g, nt, smem, st>>>(sp);
+      } else {
+        if (uni) hub_seg_kernel<true, LZ, false, 1024><<<(int)g, nt, smem, st>>>(sp);
+        else hub_seg_kernel<false, LZ, false, 1024><<<(int)g, nt, smem, st>>>(sp);
+      }
+    } else if (vec) {
+      if (uni) hub_seg_kernel<true, LZ, true, 512><<<(int)g, seg_threads, smem, st>>>(sp);
+      else hub_seg_kernel<false, LZ, true, 512><<<(int)g, seg_threads, smem, st>>>(sp);
     } else {
-      if (uni) hub_seg_kernel<true, LZ, 16><<<(int)g, seg_threads, smem, st>>>(sp);
-      else hub_seg_kernel<false, LZ, 16><<<(int)g, seg_threads, smem, st>>>(sp);
+      if (uni) hub_seg_kernel<true, LZ, false, 512><<<(int)g, seg_threads, smem, st>>>(sp);
+      else hub_seg_kernel<false, LZ, false, 512><<<(int)g, seg_threads, smem, st>>>(sp);
     }
     KERNEL_CHECK();
     return CMPY_OK;
   }
 
-  template <bool UNI, int WLL>
-  int configure_seg_inst(size_t smem) {
-    int rc = raise_smem_limit(hub_seg_kernel<UNI, false, WLL>, smem_optin);
-    if (!rc) rc = raise_smem_limit(hub_seg_kernel<UNI, true, WLL>, smem_optin);
+  template <bool UNI, bool VEC>
+  int configure_seg_inst(size_t smem, int& nb_out) {
+    int rc = raise_smem_limit(hub_seg_kernel<UNI, false, VEC, 512>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_seg_kernel<UNI, true, VEC, 512>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_seg_kernel<UNI, false, VEC, 1024>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_seg_kernel<UNI, true, VEC, 1024>, smem_optin);
     if (rc) return rc;
     int nb = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_seg_kernel<UNI, true, WLL>,
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_seg_kernel<UNI, true, VEC, 512>,
                                                            seg_threads, smem));
-    if (nb < 1) { seg.ok = false; return CMPY_OK; }
-    seg_blocks_per_sm = nb > 16 ? 16 : nb;
+    nb_out = nb;
     return CMPY_OK;
   }
 
@@ -154,17 +181,26 @@ struct HubbardOp : cmpy_op_s {
   int configure_seg(int n_dn, const int* s1, const int* s2, const double* eps) {
     int rc = build_seg_tables(seg, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, uniform);
     if (rc || !seg.ok) return rc;
-    const size_t smem = (size_t)seg.lay.bytes + sizeof(double) * (size_t)dn.num;
+    const size_t smem = seg_smem();
     if ((i64)smem > smem_optin - 4096) { seg.ok = false; return CMPY_OK; }
-    int warps = seg.lay.nitems < 32 ? seg.lay.nitems : 32;
-    // small rows: several CTAs per SM with fewer warps each
-    if (smem < 48 * 1024 && warps > 8) warps = 8;
-    if (warps < 1) warps = 1;
-    seg_threads = warps * 32;
+    // two columns per lane: enough threads to cover a row once, at most 512
+    i64 t = ((dn.num + 1) / 2 + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 512) t = 512;
+    if (smem < 40 * 1024 && t > 256) t = 256;  // small rows: several CTAs per SM
+    seg_threads = (int)t;
     const bool uni = uniform && eps_uniform;
-    if (seg.wll_pad == 8) rc = uni ? configure_seg_inst<true, 8>(smem) : configure_seg_inst<false, 8>(smem);
-    else rc = uni ? configure_seg_inst<true, 16>(smem) : configure_seg_inst<false, 16>(smem);
-    return rc;
+    int nb1 = 0, nb2 = 0;
+    if (uni) { rc = configure_seg_inst<true, true>(smem, nb1); if (!rc) rc = configure_seg_inst<true, false>(smem, nb2); }
+    else { rc = configure_seg_inst<false, true>(smem, nb1); if (!rc) rc = configure_seg_inst<false, false>(smem, nb2); }
+    if (rc) return rc;
+    int nb = nb1 < nb2 ? nb1 : nb2;
+    if (nb < 1) { seg.ok = false; return CMPY_OK; }
+    seg_blocks_per_sm = nb > 8 ? 8 : nb;
+    // long rows (one CTA per SM): 1024-thread CTAs hide the shared-memory latency chains
+    // better than 512 x 128 registers (measured on B200: 4.19 vs 4.93 ms on the 4x4 sector)
+    seg_wide = (seg_blocks_per_sm == 1 && dn.num >= 2048);
+    return CMPY_OK;
   }
 
   template <bool UNI>

@@ -11,9 +11,10 @@
 //                                segment offset + parity
 // No per-string table is ever read from global memory; the only HBM/L2 traffic is the
 // vector itself: own row once (staged in smem), the up-hop neighbour rows (coalesced),
-// and y.  One warp owns one segment at a time (lanes = rank of dl); all hop loops have
-// warp-uniform or short, fully unrolled trip counts, so each lane keeps many independent
-// loads in flight.
+// and y.  Each lane owns two adjacent columns: it first issues a batch of 16-byte up-hop
+// gathers, does the whole dn part out of shared memory while they are in flight, then
+// consumes them (memory-level parallelism without relying on occupancy: one 512-thread CTA
+// per SM, up to 128 registers per thread).
 //
 // ref for the matrix elements: cmpy/operators.py:305-527 (see hubbard.cuh).
 #pragma once
@@ -31,12 +32,13 @@ struct SegLayout {          // byte offsets into the table blob (all 16-byte ali
   int off_hi_kl;            // i8  [nhi]   popcount class of the segment, -1 invalid
   int off_cls_off;          // u16 [m+2]
   int off_lo_list;          // u8  [nlo]   class-major list of dl
-  int off_ll_cnt;           // u8  [nlo]
-  int off_ll_ent;           // u16 [nlo][wll]   (rank' | neg<<7 | bond<<8)
-  int off_hh_ptr;           // u16 [nhi+1]
-  int off_hh_ent;           // u32 [...]        (src segment offset | bond<<16 | neg<<31)
-  int off_lh_lo;            // u8  [nlh][nlo]   (rank' | parity<<7)
-  int off_lh_hi;            // u32 [nlh][nhi]   (offset of dh^bit | parity<<16 | bit<<17)
+  int off_lo_rank;          // u8  [nlo]   rank of dl inside its popcount class
+  int off_ll_cnt;           // u8  [nlo]   npos | ntot<<4
+  int off_ll_ent;           // u16 [wll][nlo]   (rank'*8 | bond<<10), '+' entries first
+  int off_hh_ptr;           // u32 [nhi+1]      start | npos<<16 | ntot<<24
+  int off_hh_ent;           // u32 [...]        (segment byte offset | bond<<24)
+  int off_lh_lo;            // u16 [nlh][nlo]   (rank'*8 | parity<<14 | bit<<15)
+  int off_lh_hi;            // u32 [nlh][nhi]   (byte offset of segment dh^bit | parity<<30 | bit<<31)
   int off_e_lo;             // f64 [nlo]  (only when !uniform)
   int off_e_hi;             // f64 [nhi]
   int bytes;
@@ -53,9 +55,107 @@ struct SegParams {
 
 struct __align__(16) UpEnt { i64 off; double coef; };
 
-// WLL = compile-time padded width of the LL entry rows (8 or 16 u16 entries)
-template <bool UNI, bool LZ, int WLL>
-__global__ void __launch_bounds__(1024, 1) hub_seg_kernel(SegParams sp) {
+// flip the sign of v when `neg` (0/1) is set, via the IEEE sign bit
+__device__ __forceinline__ double flip_sign(double v, uint32_t neg) {
+  return __hiloint2double(__double2hiint(v) ^ (int)(neg << 31), __double2loint(v));
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
+
+// All dn hops + diagonal of one amplitude (column d of the staged row).
+// Table entries hold BYTE offsets; every list is ordered "+ entries, then - entries" so no
+// per-hop sign arithmetic is needed (UNI). `xs_s` = shared-space address of xs[0].
+template <bool UNI>
+__device__ __forceinline__ double seg_dn_part(
+    const SegParams& sp, const unsigned char* tab, uint32_t xs_s, const double* s_hop,
+    const double* s_u, uint32_t ups, double eu, int d, uint32_t dns, double xi) {
+  const SegLayout& L = sp.lay;
+  const uint8_t* lo_rank = tab + L.off_lo_rank;
+  const uint8_t* ll_cnt = tab + L.off_ll_cnt;
+  const uint16_t* ll_ent = reinterpret_cast<const uint16_t*>(tab + L.off_ll_ent);
+  const uint32_t* hh_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ptr);
+  const uint32_t* hh_ent = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ent);
+  const uint16_t* lh_lo = reinterpret_cast<const uint16_t*>(tab + L.off_lh_lo);
+  const uint32_t* lh_hi = reinterpret_cast<const uint32_t*>(tab + L.off_lh_hi);
+  const int dl = (int)(dns & (uint32_t)(L.nlo - 1));
+  const int dh = (int)(dns >> L.m);
+  const int r = lo_rank[dl];
+  const uint32_t seg_s = xs_s + (uint32_t)(d - r) * 8u;  // address of the segment start
+  const uint32_t r_s = xs_s + (uint32_t)r * 8u;          // xs + r
+  double diag;
+  if (UNI) {
+    diag = eu + sp.e_dn_const + sp.hp.u0 * (double)__popc(ups & dns);
+  } else {
+    const double* e_lo = reinterpret_cast<const double*>(tab + L.off_e_lo);
+    const double* e_hi = reinterpret_cast<const double*>(tab + L.off_e_hi);
+    double w = 0.0;
+    uint32_t both = ups & dns;
+    while (both) { const int i = __ffs(both) - 1; both &= both - 1; w += s_u[i]; }
+    diag = eu + (e_hi[dh] + e_lo[dl]) + w;
+  }
+  double acc = diag * xi;
+  double hp = 0.0, hn = 0.0;  // UNI: sums of '+' and '-' neighbours
+  {  // LL hops: per-dl list, layout [q][dl] (conflict-free), entry = rank'*8 | bond<<10
+    const uint32_t c = ll_cnt[dl];
+    const int cpos = (int)(c & 15u), ctot = (int)(c >> 4);
+    const uint16_t* ep = ll_ent + dl;
+    int q = 0;
+#pragma unroll 1
+    for (; q < cpos; ++q) {
+      const uint32_t e = ep[q * L.nlo];
+      const double v = lds_f64(seg_s + (e & 0x3ffu));
+      if (UNI) hp += v; else acc += v * s_hop[e >> 10];
+    }
+#pragma unroll 1
+    for (; q < ctot; ++q) {
+      const uint32_t e = ep[q * L.nlo];
+      const double v = lds_f64(seg_s + (e & 0x3ffu));
+      if (UNI) hn += v; else acc -= v * s_hop[e >> 10];
+    }
+  }
+  {  // HH hops: per-dh list (segment byte offset | bond<<24), '+' entries then '-'
+    const uint32_t pp = hh_ptr[dh];
+    int q = (int)(pp & 0xffffu);
+    const int qpos = q + (int)((pp >> 16) & 0xffu), qtot = q + (int)(pp >> 24);
+#pragma unroll 1
+    for (; q < qpos; ++q) {
+      const uint32_t e = hh_ent[q];
+      const double v = lds_f64(r_s + (e & 0xffffffu));
+      if (UNI) hp += v; else acc += v * s_hop[e >> 24];
+    }
+#pragma unroll 1
+    for (; q < qtot; ++q) {
+      const uint32_t e = hh_ent[q];
+      const double v = lds_f64(r_s + (e & 0xffffffu));
+      if (UNI) hn += v; else acc -= v * s_hop[e >> 24];
+    }
+  }
+#pragma unroll 1
+  for (int b = 0; b < L.nlh; ++b) {  // LH hops
+    // hi: segment byte offset (bits 0-23) | parity<<30 | bit<<31 ; lo: rank'*8 | parity<<14 | bit<<15
+    const uint32_t hi = lh_hi[b * L.nhi + dh];
+    const uint32_t lo = lh_lo[b * L.nlo + dl];
+    const uint32_t t = hi ^ (lo << 16);  // bit31 = hop allowed, bit30 = negative
+    if (t >> 31) {
+      const double v = lds_f64(xs_s + (hi & 0xffffffu) + (lo & 0x3ffu));
+      const double sv = flip_sign(v, (t >> 30) & 1u);
+      if (UNI) hp += sv; else acc += sv * s_hop[L.lh_bond[b]];
+    }
+  }
+  if (UNI) acc += sp.hp.hop0 * (hp - hn);
+  return acc;
+}
+
+// NT = threads per CTA (512: <=128 regs, 8 gathers in flight per lane; 1024: <=64 regs, 4)
+
+// smem: [table blob][dn strings u32[nd_pad]][row of x: double[nd]]
+template <bool UNI, bool LZ, bool VEC2, int NT>
+__global__ void __launch_bounds__(NT, 1) hub_seg_kernel(SegParams sp) {
+  constexpr int SEG_UPG = NT <= 512 ? 8 : 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
   __shared__ UpEnt s_up[ELL_MAX_BONDS];
@@ -63,55 +163,42 @@ __global__ void __launch_bounds__(1024, 1) hub_seg_kernel(SegParams sp) {
   __shared__ double s_u[32];
   const HubParams& p = sp.hp;
   const SegLayout& L = sp.lay;
+  const i64 nd = p.num_dn, nu = p.num_up;
+  const int ndi = (int)nd;
   unsigned char* tab = smem_raw;
-  double* xs = reinterpret_cast<double*>(smem_raw + L.bytes);
+  uint32_t* s_dn = reinterpret_cast<uint32_t*>(smem_raw + L.bytes);
+  double* xs = reinterpret_cast<double*>(smem_raw + L.bytes + (((size_t)nd * 4 + 15) & ~(size_t)15));
   const int tid = threadIdx.x, nt = blockDim.x;
-  {  // table blob -> smem
+  {  // tables + dn strings -> smem (once per CTA)
     const uint4* src = reinterpret_cast<const uint4*>(sp.blob);
     uint4* dst = reinterpret_cast<uint4*>(tab);
     for (int k = tid; k < L.bytes / 16; k += nt) dst[k] = src[k];
+    for (int k = tid; k < ndi; k += nt) s_dn[k] = p.dn_states[k];
     if (tid < ELL_MAX_BONDS) s_hop[tid] = p.hop[tid];
     if (tid < 32) s_u[tid] = tid < p.num_sites ? p.u[tid] : 0.0;
   }
-  const uint32_t* items = reinterpret_cast<const uint32_t*>(tab + L.off_items);
-  const uint16_t* hi_off = reinterpret_cast<const uint16_t*>(tab + L.off_hi_off);
-  const int8_t* hi_kl = reinterpret_cast<const int8_t*>(tab + L.off_hi_kl);
-  const uint16_t* cls_off = reinterpret_cast<const uint16_t*>(tab + L.off_cls_off);
-  const uint8_t* lo_list = tab + L.off_lo_list;
-  const uint8_t* ll_cnt = tab + L.off_ll_cnt;
-  const uint16_t* ll_ent = reinterpret_cast<const uint16_t*>(tab + L.off_ll_ent);
-  const uint16_t* hh_ptr = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ptr);
-  const uint32_t* hh_ent = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ent);
-  const uint8_t* lh_lo = tab + L.off_lh_lo;
-  const uint32_t* lh_hi = reinterpret_cast<const uint32_t*>(tab + L.off_lh_hi);
-  const double* e_lo = reinterpret_cast<const double*>(tab + L.off_e_lo);
-  const double* e_hi = reinterpret_cast<const double*>(tab + L.off_e_hi);
-
   int j; double s1, s2; bool has_prev;
   lz_scalars<LZ>(p.lz, j, s1, s2, has_prev);
-  const i64 nd = p.num_dn, nu = p.num_up;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const double hop0 = p.hop0;
   double dot = 0.0;
+  const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(xs);
 
   for (i64 r_row = blockIdx.x; r_row < p.nrows; r_row += gridDim.x) {
     const i64 u = p.row0 + r_row;
     const double* __restrict__ xr = p.x + r_row * nd;
-    __syncthreads();  // previous row fully consumed (and tables loaded on first pass)
-    // ---- stage the row (vectorised when 16-byte aligned) ----
-    if (((nd & 1) == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0)) {
+    __syncthreads();  // previous row fully consumed (and tables loaded on the first pass)
+    if (VEC2) {
       const double2* x2 = reinterpret_cast<const double2*>(xr);
       double2* s2p = reinterpret_cast<double2*>(xs);
-      for (i64 d = tid; d < nd / 2; d += nt) s2p[d] = x2[d];
+      for (int d = tid; d < ndi / 2; d += nt) s2p[d] = x2[d];
     } else {
-      for (i64 d = tid; d < nd; d += nt) xs[d] = xr[d];
+      for (int d = tid; d < ndi; d += nt) xs[d] = xr[d];
     }
     const int cu = p.with_up ? (int)p.cnt_up[u] : 0;
     if (tid < cu) {
       const uint32_t e = p.ell_up[(i64)tid * nu + u];
       UpEnt ue;
       ue.off = ((i64)(e & ELL_TGT_MASK) - u) * nd;  // relative to the current row
-      const double hv = UNI ? hop0 : s_hop[(e >> ELL_TGT_BITS) & 63u];
+      const double hv = UNI ? p.hop0 : s_hop[(e >> ELL_TGT_BITS) & 63u];
       ue.coef = (e >> 31) ? -hv : hv;
       s_up[tid] = ue;
     }
@@ -120,95 +207,64 @@ __global__ void __launch_bounds__(1024, 1) hub_seg_kernel(SegParams sp) {
     const double eu = p.e_up[u];
     double* __restrict__ yr = p.y + r_row * nd;
 
-    for (int it = warp; it < L.nitems; it += nwarps) {
-      const uint32_t item = items[it];
-      const int dh = (int)(item & 0xffffu);
-      const int r = (int)(item >> 16) + lane;
-      const int kl = hi_kl[dh];
-      const int base = hi_off[dh];
-      const int cb = cls_off[kl];
-      const int len = cls_off[kl + 1] - cb;
-      const int hp0 = hh_ptr[dh], hp1 = hh_ptr[dh + 1];
-      const double ehi = UNI ? sp.e_dn_const : e_hi[dh];
-      if (r < len) {
-        const int dl = lo_list[cb + r];
-        const double xi = xs[base + r];
-        const uint32_t dns = ((uint32_t)dh << L.m) | (uint32_t)dl;
-        double diag;
-        if (UNI) {
-          diag = eu + ehi + p.u0 * (double)__popc(ups & dns);
-        } else {
-          double w = 0.0;
-          uint32_t both = ups & dns;
-          while (both) { const int i = __ffs(both) - 1; both &= both - 1; w += s_u[i]; }
-          diag = eu + (ehi + e_lo[dl]) + w;
-        }
-        double acc = diag * xi;
-        double h = 0.0;  // UNI: signed sum of neighbours, scaled by hop0 at the end
-        // ---- LL hops: compact per-dl list, entries fetched with 128-bit loads ----
-        {
-          const int c = ll_cnt[dl];
-          const uint4* ep = reinterpret_cast<const uint4*>(ll_ent + dl * WLL);
-          uint32_t w32[WLL / 2];
+    if (VEC2) {
+      for (int d = 2 * tid; d < ndi; d += 2 * nt) {
+        const double* __restrict__ xg = xr + d;
+        // ---- issue the first group of up-hop gathers (coalesced 16 B per lane) ----
+        double2 g[SEG_UPG];
 #pragma unroll
-          for (int q = 0; q < WLL / 8; ++q) {
-            const uint4 t4 = ep[q];
-            w32[4 * q] = t4.x; w32[4 * q + 1] = t4.y; w32[4 * q + 2] = t4.z; w32[4 * q + 3] = t4.w;
-          }
+        for (int k = 0; k < SEG_UPG; ++k)
+          if (k < cu) g[k] = __ldg(reinterpret_cast<const double2*>(xg + s_up[k].off));
+        // ---- dn part for both columns (shared memory only) ----
+        const double2 xi = *reinterpret_cast<const double2*>(xs + d);
+        const uint2 dn2 = *reinterpret_cast<const uint2*>(s_dn + d);
+        double a0 = seg_dn_part<UNI>(sp, tab, xs_s, s_hop, s_u, ups, eu, d, dn2.x, xi.x);
+        double a1 = seg_dn_part<UNI>(sp, tab, xs_s, s_hop, s_u, ups, eu, d + 1, dn2.y, xi.y);
+        // ---- consume the gathers, then the remaining up hops ----
 #pragma unroll
-          for (int q = 0; q < WLL; ++q) {
-            if (q < c) {
-              const uint32_t e = (w32[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-              const double v = xs[base + (int)(e & 127u)];
-              const double sv = (e & 128u) ? -v : v;
-              if (UNI) h += sv; else acc += sv * s_hop[e >> 8];
-            }
-          }
+        for (int k = 0; k < SEG_UPG; ++k)
+          if (k < cu) { const double c = s_up[k].coef; a0 += c * g[k].x; a1 += c * g[k].y; }
+        for (int k0 = SEG_UPG; k0 < cu; k0 += SEG_UPG) {
+#pragma unroll
+          for (int k = 0; k < SEG_UPG; ++k)
+            if (k0 + k < cu) g[k] = __ldg(reinterpret_cast<const double2*>(xg + s_up[k0 + k].off));
+#pragma unroll
+          for (int k = 0; k < SEG_UPG; ++k)
+            if (k0 + k < cu) { const double c = s_up[k0 + k].coef; a0 += c * g[k].x; a1 += c * g[k].y; }
         }
-        // ---- HH hops: warp-uniform list, whole-segment shifts ----
-        for (int q = hp0; q < hp1; ++q) {
-          const uint32_t e = hh_ent[q];
-          const double v = xs[(int)(e & 0xffffu) + r];
-          const double sv = (e >> 31) ? -v : v;
-          if (UNI) h += sv; else acc += sv * s_hop[(e >> 16) & 63u];
-        }
-        // ---- LH hops ----
-        for (int b = 0; b < L.nlh; ++b) {
-          const uint32_t hi = lh_hi[b * L.nhi + dh];
-          const uint32_t lo = lh_lo[b * L.nlo + dl];
-          const uint32_t bit_lo = ((uint32_t)dl >> L.lh_lobit[b]) & 1u;
-          const uint32_t bit_hi = (hi >> 17) & 1u;
-          if (bit_lo != bit_hi) {
-            const double v = xs[(int)(hi & 0xffffu) + (int)(lo & 127u)];
-            const double sv = (((lo >> 7) ^ (hi >> 16)) & 1u) ? -v : v;
-            if (UNI) h += sv; else acc += sv * s_hop[L.lh_bond[b]];
-          }
-        }
-        if (UNI) acc += hop0 * h;
-        // ---- up hops: coalesced gathers from neighbour rows (L2 / HBM) ----
-        {
-          const double* __restrict__ xg = xr + base + r;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          int k = 0;
-          for (; k + 4 <= cu; k += 4) {
-            const UpEnt e0 = s_up[k], e1 = s_up[k + 1], e2 = s_up[k + 2], e3 = s_up[k + 3];
-            const double v0 = __ldg(xg + e0.off), v1 = __ldg(xg + e1.off);
-            const double v2 = __ldg(xg + e2.off), v3 = __ldg(xg + e3.off);
-            a0 += e0.coef * v0; a1 += e1.coef * v1; a2 += e2.coef * v2; a3 += e3.coef * v3;
-          }
-          for (; k < cu; ++k) {
-            const UpEnt e0 = s_up[k];
-            a0 += e0.coef * __ldg(xg + e0.off);
-          }
-          acc += (a0 + a1) + (a2 + a3);
-        }
+        double2* yp = reinterpret_cast<double2*>(yr + d);
         if (LZ) {
-          double w = s1 * acc;
-          if (has_prev) w -= s2 * yr[base + r];
-          yr[base + r] = w;
+          double w0 = s1 * a0, w1 = s1 * a1;
+          if (has_prev) { const double2 yo = *yp; w0 -= s2 * yo.x; w1 -= s2 * yo.y; }
+          *yp = make_double2(w0, w1);
+          dot += (s1 * xi.x) * w0 + (s1 * xi.y) * w1;
+        } else if (p.accumulate) {
+          const double2 yo = *yp;
+          *yp = make_double2(yo.x + a0, yo.y + a1);
+        } else {
+          *yp = make_double2(a0, a1);
+        }
+      }
+    } else {
+      for (int d = tid; d < ndi; d += nt) {
+        const double* __restrict__ xg = xr + d;
+        const double xi = xs[d];
+        double a0 = seg_dn_part<UNI>(sp, tab, xs_s, s_hop, s_u, ups, eu, d, s_dn[d], xi);
+        double b0 = 0.0, b1 = 0.0;
+        int k = 0;
+        for (; k + 2 <= cu; k += 2) {
+          const UpEnt e0 = s_up[k], e1 = s_up[k + 1];
+          b0 += e0.coef * __ldg(xg + e0.off); b1 += e1.coef * __ldg(xg + e1.off);
+        }
+        if (k < cu) { const UpEnt e0 = s_up[k]; b0 += e0.coef * __ldg(xg + e0.off); }
+        a0 += b0 + b1;
+        if (LZ) {
+          double w = s1 * a0;
+          if (has_prev) w -= s2 * yr[d];
+          yr[d] = w;
           dot += (s1 * xi) * w;
         } else {
-          yr[base + r] = p.accumulate ? yr[base + r] + acc : acc;
+          yr[d] = p.accumulate ? yr[d] + a0 : a0;
         }
       }
     }
@@ -294,43 +350,52 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
   auto parity = [&](u64 state, int a, int b2) {
     return __builtin_popcountll(state & between_mask(a, b2, sign_width)) & 1;
   };
-  // LL: per dl compact list
+  // LL: per dl compact list, '+' entries first; entry = rank'*8 | bond<<10
   std::vector<uint8_t> ll_cnt(nlo, 0);
   std::vector<std::vector<uint16_t>> ll_rows(nlo);
   int wll = 0;
   for (int dl = 0; dl < nlo; ++dl) {
+    std::vector<uint16_t> pos, negl;
     for (int b : ll) {
       const int b1 = (dl >> s1[b]) & 1, b2 = (dl >> s2[b]) & 1;
       if (b1 == b2) continue;
       const int nl = dl ^ (1 << s1[b]) ^ (1 << s2[b]);
       const int neg = parity((u64)dl, s1[b], s2[b]);  // bits between lie inside dl
-      ll_rows[dl].push_back((uint16_t)(lo_rank[nl] | (neg << 7) | (b << 8)));
+      (neg ? negl : pos).push_back((uint16_t)((lo_rank[nl] * 8) | (b << 10)));
     }
-    ll_cnt[dl] = (uint8_t)ll_rows[dl].size();
+    ll_rows[dl] = pos;
+    ll_rows[dl].insert(ll_rows[dl].end(), negl.begin(), negl.end());
+    if (ll_rows[dl].size() > 15) return CMPY_OK;
+    ll_cnt[dl] = (uint8_t)(pos.size() | (ll_rows[dl].size() << 4));
     wll = std::max(wll, (int)ll_rows[dl].size());
   }
-  if (wll > 16) return CMPY_OK;
-  T.wll_pad = wll <= 8 ? 8 : 16;
+  T.wll_pad = wll < 1 ? 1 : wll;
   L.wll = T.wll_pad;
-  // HH: per dh list
-  std::vector<uint16_t> hh_ptr(nhi + 1, 0);
+  // HH: per dh list, '+' entries first; entry = segment byte offset | bond<<24;
+  // hh_ptr[dh] = start | npos<<16 | ntot<<24
+  std::vector<uint32_t> hh_ptr(nhi + 1, 0);
   std::vector<uint32_t> hh_ent;
   for (int dh = 0; dh < nhi; ++dh) {
-    hh_ptr[dh] = (uint16_t)hh_ent.size();
-    if (hi_kl[dh] < 0) continue;
-    for (int b : hh) {
-      const int a = s1[b] - m, c = s2[b] - m;
-      const int b1 = (dh >> a) & 1, b2 = (dh >> c) & 1;
-      if (b1 == b2) continue;
-      const int nh = dh ^ (1 << a) ^ (1 << c);
-      const int neg = parity((u64)dh << m, s1[b], s2[b]);
-      hh_ent.push_back((uint32_t)hi_off[nh] | ((uint32_t)b << 16) | ((uint32_t)neg << 31));
+    const size_t start = hh_ent.size();
+    if (start >= 65535) return CMPY_OK;
+    std::vector<uint32_t> pos, negl;
+    if (hi_kl[dh] >= 0) {
+      for (int b : hh) {
+        const int a = s1[b] - m, c = s2[b] - m;
+        const int b1 = (dh >> a) & 1, b2 = (dh >> c) & 1;
+        if (b1 == b2) continue;
+        const int nh = dh ^ (1 << a) ^ (1 << c);
+        const int neg = parity((u64)dh << m, s1[b], s2[b]);
+        (neg ? negl : pos).push_back((uint32_t)(hi_off[nh] * 8) | ((uint32_t)b << 24));
+      }
     }
-    if (hh_ent.size() >= 65535) return CMPY_OK;
+    if (pos.size() + negl.size() > 255) return CMPY_OK;
+    hh_ptr[dh] = (uint32_t)start | ((uint32_t)pos.size() << 16) | ((uint32_t)(pos.size() + negl.size()) << 24);
+    hh_ent.insert(hh_ent.end(), pos.begin(), pos.end());
+    hh_ent.insert(hh_ent.end(), negl.begin(), negl.end());
   }
-  hh_ptr[nhi] = (uint16_t)hh_ent.size();
   // LH
-  std::vector<uint8_t> lh_lo((size_t)std::max(1, L.nlh) * nlo, 0);
+  std::vector<uint16_t> lh_lo((size_t)std::max(1, L.nlh) * nlo, 0);
   std::vector<uint32_t> lh_hi((size_t)std::max(1, L.nlh) * nhi, 0);
   for (int q = 0; q < L.nlh; ++q) {
     const int b = lh[q];
@@ -339,7 +404,8 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
     for (int dl = 0; dl < nlo; ++dl) {
       const int nl = dl ^ (1 << a);
       const int par = parity((u64)dl, a, m);  // bits of dl strictly above a (below site m)
-      lh_lo[(size_t)q * nlo + dl] = (uint8_t)(lo_rank[nl] | (par << 7));
+      const int bit_lo = (dl >> a) & 1;
+      lh_lo[(size_t)q * nlo + dl] = (uint16_t)((lo_rank[nl] * 8) | (par << 14) | (bit_lo << 15));
     }
     for (int dh = 0; dh < nhi; ++dh) {
       const int nh = dh ^ (1 << c);
@@ -347,7 +413,7 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
       // bits of dh strictly below c, i.e. sites m .. s2-1, limited to the sign width
       const int par = parity((u64)dh << m, m - 1, s2[b]);
       const int off = (nh < nhi && hi_kl[nh] >= 0) ? hi_off[nh] : 0;
-      lh_hi[(size_t)q * nhi + dh] = (uint32_t)off | ((uint32_t)par << 16) | ((uint32_t)bit << 17);
+      lh_hi[(size_t)q * nhi + dh] = (uint32_t)(off * 8) | ((uint32_t)par << 30) | ((uint32_t)bit << 31);
     }
   }
   // energies
@@ -367,11 +433,12 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
   L.off_hi_kl = o; o = align16(o + nhi);
   L.off_cls_off = o; o = align16(o + 2 * (m + 2));
   L.off_lo_list = o; o = align16(o + nlo);
+  L.off_lo_rank = o; o = align16(o + nlo);
   L.off_ll_cnt = o; o = align16(o + nlo);
   L.off_ll_ent = o; o = align16(o + 2 * nlo * L.wll);
-  L.off_hh_ptr = o; o = align16(o + 2 * (nhi + 1));
+  L.off_hh_ptr = o; o = align16(o + 4 * (nhi + 1));
   L.off_hh_ent = o; o = align16(o + 4 * (int)std::max<size_t>(1, hh_ent.size()));
-  L.off_lh_lo = o; o = align16(o + std::max(1, L.nlh) * nlo);
+  L.off_lh_lo = o; o = align16(o + 2 * std::max(1, L.nlh) * nlo);
   L.off_lh_hi = o; o = align16(o + 4 * std::max(1, L.nlh) * nhi);
   L.off_e_lo = o; o = align16(o + 8 * nlo);
   L.off_e_hi = o; o = align16(o + 8 * nhi);
@@ -383,15 +450,16 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
   { std::vector<int8_t> t(nhi); for (int i = 0; i < nhi; ++i) t[i] = (int8_t)hi_kl[i]; memcpy(&blob[L.off_hi_kl], t.data(), nhi); }
   { std::vector<uint16_t> t(m + 2); for (int i = 0; i < m + 2; ++i) t[i] = (uint16_t)cls_off[i]; memcpy(&blob[L.off_cls_off], t.data(), 2 * (m + 2)); }
   memcpy(&blob[L.off_lo_list], lo_list.data(), nlo);
+  { std::vector<uint8_t> t(nlo); for (int i = 0; i < nlo; ++i) t[i] = (uint8_t)lo_rank[i]; memcpy(&blob[L.off_lo_rank], t.data(), nlo); }
   memcpy(&blob[L.off_ll_cnt], ll_cnt.data(), nlo);
   {
-    uint16_t* dst = reinterpret_cast<uint16_t*>(&blob[L.off_ll_ent]);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(&blob[L.off_ll_ent]);  // layout [q][dl]
     for (int dl = 0; dl < nlo; ++dl)
-      for (size_t q = 0; q < ll_rows[dl].size(); ++q) dst[dl * L.wll + q] = ll_rows[dl][q];
+      for (size_t q = 0; q < ll_rows[dl].size(); ++q) dst[q * nlo + dl] = ll_rows[dl][q];
   }
-  memcpy(&blob[L.off_hh_ptr], hh_ptr.data(), 2 * (nhi + 1));
+  memcpy(&blob[L.off_hh_ptr], hh_ptr.data(), 4 * (nhi + 1));
   if (!hh_ent.empty()) memcpy(&blob[L.off_hh_ent], hh_ent.data(), 4 * hh_ent.size());
-  memcpy(&blob[L.off_lh_lo], lh_lo.data(), lh_lo.size());
+  memcpy(&blob[L.off_lh_lo], lh_lo.data(), 2 * lh_lo.size());
   memcpy(&blob[L.off_lh_hi], lh_hi.data(), 4 * lh_hi.size());
   memcpy(&blob[L.off_e_lo], e_lo.data(), 8 * nlo);
   memcpy(&blob[L.off_e_hi], e_hi.data(), 8 * nhi);

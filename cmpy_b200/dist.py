@@ -1,0 +1,211 @@
+# -*- coding: utf-8 -*-
+"""Up-string-sharded Hubbard H.v across the GPUs of one box.
+
+The amplitude matrix X (num_up x num_dn, row-major: idx = up_idx*num_dn + dn_idx, reference
+cmpy/operators.py:33-90) is split into contiguous slabs of up-rows, one slab per rank
+(one process per GPU, ``torch.distributed``).  Diagonal and dn-hops act inside a row, so
+they are local; up-hops couple rows, so they are applied in the transposed (dn-major)
+layout, where they are again row-local:
+
+  1. y_local  = (D + T_dn) x_local                         local kernel (slab of up-rows)
+  2. pack     : X[R_p, C_q] -> (C_q x R_p) blocks          transpose kernel, one block per peer
+  3. exchange : all-to-all (NCCL, grouped send/recv)       -> rank q holds X^T[C_q, :]
+  4. place    : blocks -> XT_local (|C_q| x num_up)        pitched copy kernel
+  5. YT_local = T_up XT_local                              same local kernel, roles swapped
+  6. pack / exchange / accumulate back into y_local        transpose + all-to-all + copy2d(+=)
+
+Two transposes per H.v move 2 * 8 * dim * (P-1)/P bytes over NVLink.  The reference has no
+distributed path at all; results are checked against the single-GPU operator / the oracle.
+
+The exchange choreography is independent of the device kernels: ``LocalBackend`` objects
+provide the four local primitives, so the same code runs under ``gloo`` on CPU in
+tests/ with a checker backend (no product path uses that).
+"""
+import numpy as np
+
+from . import _lib
+
+__all__ = ["ShardPlan", "ShardedHubbardOperator", "CudaBackend"]
+
+
+class ShardPlan:
+    """Balanced contiguous partition of the up-rows (and, for the transposed phase, of the
+    dn-columns) over ``world`` ranks."""
+
+    def __init__(self, num_up, num_dn, world, rank):
+        self.num_up, self.num_dn, self.world, self.rank = int(num_up), int(num_dn), int(world), int(rank)
+        self.row_bounds = [(self.num_up * k) // self.world for k in range(self.world + 1)]
+        self.col_bounds = [(self.num_dn * k) // self.world for k in range(self.world + 1)]
+
+    def rows(self, p=None):
+        p = self.rank if p is None else p
+        return self.row_bounds[p], self.row_bounds[p + 1]
+
+    def cols(self, q=None):
+        q = self.rank if q is None else q
+        return self.col_bounds[q], self.col_bounds[q + 1]
+
+    @property
+    def nrows(self):
+        r0, r1 = self.rows()
+        return r1 - r0
+
+    @property
+    def ncols(self):
+        c0, c1 = self.cols()
+        return c1 - c0
+
+    @property
+    def local_size(self):
+        return self.nrows * self.num_dn
+
+    @property
+    def local_size_t(self):
+        return self.ncols * self.num_up
+
+    def fwd_send_counts(self):
+        """elements sent to each peer q in the forward transpose: |R_p| * |C_q|"""
+        return [self.nrows * (self.cols(q)[1] - self.cols(q)[0]) for q in range(self.world)]
+
+    def fwd_recv_counts(self):
+        """elements received from each peer p: |C_q| * |R_p| (q = this rank)"""
+        return [self.ncols * (self.rows(p)[1] - self.rows(p)[0]) for p in range(self.world)]
+
+    def bytes_out_per_hv(self):
+        """bytes leaving this GPU per H.v (two transposes, own block excluded)"""
+        own = self.nrows * self.ncols
+        return 8 * ((self.local_size - own) + (self.local_size_t - own))
+
+
+class CudaBackend:
+    """Local primitives on the device through the C ABI."""
+
+    def __init__(self, op_main, op_t):
+        self.op_main, self.op_t = op_main, op_t
+        self.torch = _lib.require_cuda()
+
+    def empty(self, n):
+        return self.torch.empty(max(int(n), 1), dtype=self.torch.float64, device=_lib.device())
+
+    def apply_rows(self, x, row0, nrows, out):
+        return self.op_main.apply_rows(x, row0, nrows, out=out)
+
+    def apply_rows_t(self, xt, col0, ncols, out):
+        return self.op_t.apply_rows(xt, col0, ncols, out=out)
+
+    def transpose(self, src, src_off, nrows, ncols, ld_in, dst, dst_off, ld_out):
+        esz = 8
+        _lib.check(_lib.lib().cmpy_transpose(
+            _lib.c_void_p(src.data_ptr() + esz * src_off), nrows, ncols, ld_in,
+            _lib.c_void_p(dst.data_ptr() + esz * dst_off), ld_out, 0, _lib.stream_ptr()), "cmpy_transpose")
+
+    def copy2d(self, src, src_off, nrows, ncols, ld_in, dst, dst_off, ld_out, accumulate):
+        esz = 8
+        _lib.check(_lib.lib().cmpy_copy2d(
+            _lib.c_void_p(src.data_ptr() + esz * src_off), nrows, ncols, ld_in,
+            _lib.c_void_p(dst.data_ptr() + esz * dst_off), ld_out, int(accumulate), _lib.stream_ptr()),
+            "cmpy_copy2d")
+
+
+class ShardedHubbardOperator:
+    """H.v on the slab of up-rows owned by this rank; ``apply_local(x_local)`` returns
+    ``(H x)_local``.  ``model`` is a ``HubbardModel`` / ``SingleImpurityAndersonModel``."""
+
+    def __init__(self, model, n_up, n_dn, group=None, backend=None, up_states=None, dn_states=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.model = model
+        spec = model._operator_spec()
+        if backend is None:
+            from .operators import SectorHamiltonOperator
+
+            sector = model.basis.get_sector(n_up, n_dn)
+            up_states, dn_states = np.asarray(sector.up_states), np.asarray(sector.dn_states)
+            nsites = model.num_sites
+            op_main = SectorHamiltonOperator(nsites, up_states, dn_states, spec["bonds"], spec["hops"],
+                                             spec["eps"], spec["u"], spec["sign_width"])
+            zeros = np.zeros(nsites)
+            # transposed phase: rows = dn strings, "dn hops" of that operator = up hops of H
+            op_t = SectorHamiltonOperator(nsites, dn_states, up_states, spec["bonds"], spec["hops"],
+                                          zeros, zeros, spec["sign_width"])
+            backend = CudaBackend(op_main, op_t)
+        self.backend = backend
+        self.plan = ShardPlan(len(up_states), len(dn_states), self.world, self.rank)
+        size = self.plan.num_up * self.plan.num_dn
+        self.shape = (size, size)
+        p = self.plan
+        self._send = backend.empty(max(p.local_size, p.local_size_t))
+        self._recv = backend.empty(max(p.local_size, p.local_size_t))
+        self._xt = backend.empty(p.local_size_t)
+        self._yt = backend.empty(p.local_size_t)
+        self._pinned_out = None
+
+    @property
+    def local_size(self):
+        return self.plan.local_size
+
+    def _all_to_all(self, recv, send, recv_counts, send_counts):
+        if self.world == 1:
+            recv[: send_counts[0]].copy_(send[: send_counts[0]])
+            return
+        self.dist.all_to_all_single(recv[: sum(recv_counts)], send[: sum(send_counts)],
+                                    output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                                    group=self.group)
+
+    def apply_local(self, x_local, out=None):
+        p, be = self.plan, self.backend
+        r0, _ = p.rows()
+        c0, _ = p.cols()
+        nrows, ncols, nu, nd = p.nrows, p.ncols, p.num_up, p.num_dn
+        if out is None:
+            out = be.empty(p.local_size)
+        # 1. local phase: diagonal + dn hops
+        be.apply_rows(x_local, r0, nrows, out)
+        # 2. pack transposed blocks, one per peer
+        send_counts, recv_counts = p.fwd_send_counts(), p.fwd_recv_counts()
+        off = 0
+        for q in range(self.world):
+            q0, q1 = p.cols(q)
+            be.transpose(x_local, q0, nrows, q1 - q0, nd, self._send, off, nrows)
+            off += send_counts[q]
+        # 3. exchange
+        self._all_to_all(self._recv, self._send, recv_counts, send_counts)
+        # 4. place the blocks into the dn-major slab XT (ncols x num_up)
+        off = 0
+        for src in range(self.world):
+            s0, s1 = p.rows(src)
+            be.copy2d(self._recv, off, ncols, s1 - s0, s1 - s0, self._xt, s0, nu, False)
+            off += recv_counts[src]
+        # 5. up hops, row-local in the transposed layout
+        be.apply_rows_t(self._xt, c0, ncols, self._yt)
+        # 6. way back: pack (transpose), exchange, accumulate into y
+        off = 0
+        for dst in range(self.world):
+            d0, d1 = p.rows(dst)
+            be.transpose(self._yt, d0, ncols, d1 - d0, nu, self._send, off, ncols)
+            off += recv_counts[dst]
+        self._all_to_all(self._recv, self._send, send_counts, recv_counts)
+        off = 0
+        for q in range(self.world):
+            q0, q1 = p.cols(q)
+            be.copy2d(self._recv, off, nrows, q1 - q0, q1 - q0, out, q0, nd, True)
+            off += send_counts[q]
+        return out
+
+    def matvec(self, x_local):
+        """Public call on the local slab: CUDA tensor in -> CUDA tensor out; CPU (pinned)
+        tensor in -> pinned CPU tensor out (H2D + H.v + D2H)."""
+        torch = _lib.require_cuda()
+        if x_local.is_cuda:
+            return self.apply_local(x_local)
+        dev = x_local.to(_lib.device(), non_blocking=True)
+        y = self.apply_local(dev)
+        if self._pinned_out is None:
+            self._pinned_out = torch.empty(self.local_size, dtype=torch.float64).pin_memory()
+        self._pinned_out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pinned_out

@@ -51,11 +51,12 @@ class LanczosResult:
 
 
 def _start_vector(size, seed=0):
+    """Seeded standard-normal start vector, normalised, generated on the device."""
     torch = _lib.require_cuda()
-    g = torch.Generator(device="cpu")
+    g = torch.Generator(device=_lib.device())
     g.manual_seed(seed)
-    v = torch.randn(size, dtype=torch.float64, generator=g)
-    return (v / v.norm()).to(_lib.device())
+    v = torch.randn(size, dtype=torch.float64, device=_lib.device(), generator=g)
+    return v / v.norm()
 
 
 def lanczos_run(hamop, v0=None, maxit=500, tol=1e-10, resid_tol=0.0, check_every=10,

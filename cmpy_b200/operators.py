@@ -271,6 +271,17 @@ class _DeviceOperatorMixin:
     def _apply_any(self, x):
         """numpy in -> numpy out (host round trip); CUDA tensor in -> CUDA tensor out."""
         torch = _lib.require_cuda()
+        if isinstance(x, torch.Tensor) and not x.is_cuda and not x.is_complex():
+            # host tensor (pinned memory = fast path): H2D, H.v, D2H into a pinned buffer
+            dev = x.to(device=_lib.device(), dtype=torch.float64, non_blocking=True)
+            y = self.apply(dev)
+            out = getattr(self, "_pinned_out", None)
+            if out is None or out.numel() != y.numel():
+                out = torch.empty(y.numel(), dtype=torch.float64).pin_memory()
+                self._pinned_out = out
+            out.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out.view(x.shape)
         if isinstance(x, torch.Tensor):
             if x.is_complex():
                 xr = torch.view_as_real(x.contiguous().view(-1))

@@ -120,7 +120,8 @@ int cmpy_hv_apply(cmpy_op_t op, const double* d_x, double* d_y, void* stream);
 int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_y_slab,
                             int64_t row0, int64_t nrows, int accumulate, void* stream);
 /* Which H.v kernel variant cmpy_hv_apply uses: 0 = auto, 1 = global-gather,
- * 2 = shared-memory row staging.  (Profiling / tests only.) */
+ * 2 = shared-memory row staging with per-string tables, 3 / 4 = two-level segment kernel
+ * with 512 / 1024 threads per CTA.  (Profiling / tests only.) */
 int cmpy_hv_set_variant(cmpy_op_t op, int variant);
 /* trace(H) = sum of the diagonal.  ref: HamiltonOperator._trace cmpy/operators.py:641-646.
  * Synchronous. */
@@ -177,9 +178,14 @@ int cmpy_pole_sum(const double* d_weights, const double* d_poles, int64_t npoles
                   const double* d_z, int64_t nz, double* d_g, int accumulate, void* stream);
 
 /* ---- K9 building blocks: slab transposes for the up-string-sharded H.v ---------- */
-/* out[c*nrows + r] = in[r*ld_in + c] for r < nrows, c < ncols (tiled smem transpose). */
+/* out[c*ld_out + r] (+)= in[r*ld_in + c] for r < nrows, c < ncols (tiled smem transpose).
+ * Packs a (rows x cols) block of the row-major amplitude slab into the dn-major layout that
+ * the all-to-all exchanges. */
 int cmpy_transpose(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
-                   double* d_out, int accumulate, void* stream);
+                   double* d_out, int64_t ld_out, int accumulate, void* stream);
+/* out[r*ld_out + c] (+)= in[r*ld_in + c]: places / accumulates a received block. */
+int cmpy_copy2d(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
+                double* d_out, int64_t ld_out, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,130 @@
+"""World-size-2 (and 3) gloo tests of the up-string-sharded H.v choreography on CPU: the
+exchange/packing logic of cmpy_b200.dist runs unchanged; the four local device primitives are
+replaced by a checker backend built on the oracle (tests only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_np as orc
+from conftest import ROOT
+
+
+class OracleBackend:
+    """CPU stand-in for the CUDA kernels (apply_rows / transpose / copy2d)."""
+
+    def __init__(self, up, dn, nb, inter, eps, hop, L):
+        self.up, self.dn = up, dn
+        nu, nd = len(up), len(dn)
+        # diagonal + dn hops as a dense (nd x nd) operator per row, up hops as (nu x nu)
+        self.e_up = orc.weighted_elements(up, np.full(L, eps))
+        self.e_dn = orc.weighted_elements(dn, np.full(L, eps))
+        self.inter = inter
+        self.t_dn = np.zeros((nd, nd)); self.t_up = np.zeros((nu, nu))
+        for i, j in nb:
+            o, t, s = orc.species_hops(dn, L, i, j)
+            np.add.at(self.t_dn, (t, o), s * hop)
+            o, t, s = orc.species_hops(up, L, i, j)
+            np.add.at(self.t_up, (t, o), s * hop)
+
+    def empty(self, n):
+        return torch.zeros(max(int(n), 1), dtype=torch.float64)
+
+    def apply_rows(self, x, row0, nrows, out):
+        nd = len(self.dn)
+        X = x[: nrows * nd].view(nrows, nd).numpy()
+        ups = self.up[row0:row0 + nrows]
+        docc = np.array([[int(a & b).bit_count() for b in self.dn] for a in ups])
+        Y = (self.e_up[row0:row0 + nrows, None] + self.e_dn[None, :] + self.inter * docc) * X + X @ self.t_dn.T
+        out[: nrows * nd] = torch.from_numpy(Y.reshape(-1))
+        return out
+
+    def apply_rows_t(self, xt, col0, ncols, out):
+        nu = len(self.up)
+        XT = xt[: ncols * nu].view(ncols, nu).numpy()
+        out[: ncols * nu] = torch.from_numpy((XT @ self.t_up.T).reshape(-1))
+        return out
+
+    def transpose(self, src, src_off, nrows, ncols, ld_in, dst, dst_off, ld_out):
+        s = torch.as_strided(src, (nrows, ncols), (ld_in, 1), src_off)
+        d = torch.as_strided(dst, (ncols, nrows), (ld_out, 1), dst_off)
+        d.copy_(s.t())
+
+    def copy2d(self, src, src_off, nrows, ncols, ld_in, dst, dst_off, ld_out, accumulate):
+        s = torch.as_strided(src, (nrows, ncols), (ld_in, 1), src_off)
+        d = torch.as_strided(dst, (nrows, ncols), (ld_out, 1), dst_off)
+        if accumulate:
+            d.add_(s)
+        else:
+            d.copy_(s)
+
+
+class _Model:
+    def _operator_spec(self):
+        return {}
+
+
+def _worker(rank, world, port, L, nu, nd, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cmpy_b200.dist import ShardedHubbardOperator
+
+        nb = orc.chain_neighbors(L, periodic=True)
+        up, dn = orc.enumerate_states(L, nu), orc.enumerate_states(L, nd)
+        be = OracleBackend(up, dn, nb, 4.0, -2.0, 1.0, L)
+        op = ShardedHubbardOperator(_Model(), nu, nd, backend=be, up_states=up, dn_states=dn)
+        x = np.random.default_rng(0).standard_normal(len(up) * len(dn))
+        ref = orc.hubbard_matvec_free(up, dn, nb, 4.0, -2.0, 1.0, x, width=L)
+        r0, r1 = op.plan.rows()
+        xl = torch.from_numpy(x[r0 * len(dn): r1 * len(dn)].copy())
+        yl = op.apply_local(xl).numpy()[: (r1 - r0) * len(dn)]
+        err = np.abs(yl - ref[r0 * len(dn): r1 * len(dn)]).max() / np.abs(ref).max()
+        # second application reuses the buffers
+        yl2 = op.apply_local(xl).numpy()[: (r1 - r0) * len(dn)]
+        ok = err < 1e-13 and np.array_equal(yl, yl2)
+        t = torch.tensor([1.0 if ok else 0.0])
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put((float(t.item()), float(err), op.plan.bytes_out_per_hv()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,L,nu,nd", [(2, 6, 3, 3), (2, 5, 2, 3), (3, 6, 3, 2)])
+def test_sharded_hv_gloo(world, L, nu, nd):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 200) + world * 7 + L
+    procs = [ctx.Process(target=_worker, args=(r, world, port, L, nu, nd, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ok, err, nbytes = ret.get(timeout=10)
+    assert ok == 1.0, err
+    assert nbytes > 0
+
+
+def test_shard_plan_host():
+    from cmpy_b200.dist import ShardPlan
+
+    for world in (1, 2, 3, 8):
+        plans = [ShardPlan(12870, 12870, world, r) for r in range(world)]
+        assert sum(p.nrows for p in plans) == 12870 and sum(p.ncols for p in plans) == 12870
+        for p in plans:
+            assert sum(p.fwd_send_counts()) == p.local_size
+            assert sum(p.fwd_recv_counts()) == p.local_size_t
+        for a in plans:
+            for b in plans:  # what a sends to b is what b expects from a
+                assert a.fwd_send_counts()[b.rank] == b.fwd_recv_counts()[a.rank]
+    p = ShardPlan(184756, 184756, 8, 0)
+    # 29.9 GB out per GPU per transpose at L=20
+    assert abs(p.bytes_out_per_hv() / 2 / 1e9 - 29.87) < 0.1

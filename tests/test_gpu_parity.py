@@ -650,3 +650,52 @@ def test_heisenberg_xx_chain_n32_c3(cm):
     e_ref = np.linalg.eigvalsh(a)[: N // 2].sum()
     res = lanczos_run(h, None, maxit=400, tol=1e-11, resid_tol=0.0, check_every=20)
     assert abs(res.e0 - e_ref) < E0_TOL
+
+
+# ---------------------------------------------------------------------------------------
+# K9: sharded H.v building blocks (single process; the exchange itself is covered by the
+# gloo tests on CPU and by bench.py --gpus N)
+# ---------------------------------------------------------------------------------------
+
+def test_sharded_operator_world1_matches_single(cm):
+    import torch
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.dist import ShardedHubbardOperator
+
+    for L, nb, nu, nd in [(10, chain(10, True), 5, 5), (9, orc.square_neighbors(3, 3), 4, 3), (12, chain(12), 6, 6)]:
+        model = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0)
+        h = model.hamilton_operator(nu, nd)
+        sh = ShardedHubbardOperator(model, nu, nd)
+        x = torch.randn(h.shape[0], dtype=torch.float64, device="cuda")
+        ref = h.apply(x)
+        got = sh.apply_local(x)
+        assert float((got - ref).abs().max()) < 1e-12 * float(ref.abs().max())
+        yh = sh.matvec(x.cpu().pin_memory())
+        assert not yh.is_cuda and float((yh - ref.cpu()).abs().max()) < 1e-12 * float(ref.abs().max())
+
+
+def test_transpose_copy2d_kernels(cm):
+    import torch
+    from cmpy_b200 import _lib
+
+    a = torch.randn(70, 131, dtype=torch.float64, device="cuda")
+    out = torch.zeros(50, 90, dtype=torch.float64, device="cuda")
+    # block rows 3..63, cols 11..58 of `a`, transposed into out[:48, 5:65]
+    _lib.check(_lib.lib().cmpy_transpose(_lib.c_void_p(a.data_ptr() + 8 * (3 * 131 + 11)), 60, 47, 131,
+                                         _lib.c_void_p(out.data_ptr() + 8 * 5), 90, 0, _lib.stream_ptr()))
+    assert torch.equal(out[:47, 5:65], a[3:63, 11:58].t())
+    acc = torch.ones(60, 47, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().cmpy_copy2d(_lib.c_void_p(a.data_ptr() + 8 * (3 * 131 + 11)), 60, 47, 131,
+                                      _lib.ptr(acc), 47, 1, _lib.stream_ptr()))
+    assert torch.equal(acc, a[3:63, 11:58] + 1.0)
+
+
+def test_host_tensor_matvec(cm):
+    import torch
+    from cmpy_b200.models import HubbardModel
+
+    h = HubbardModel(8, chain(8), inter=4.0, mu=2.0, hop=1.0).hamilton_operator(4, 4)
+    x = torch.randn(4900, dtype=torch.float64).pin_memory()
+    y = h.matvec(x)
+    assert not y.is_cuda
+    assert float((y - h.matvec(x.cuda()).cpu()).abs().max()) == 0.0

@@ -17,7 +17,7 @@ def timeit(fn, n=10, warm=3):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
-def run(name, L, nb, nu, nd, variants=(1, 2, 3), n=10):
+def run(name, L, nb, nu, nd, variants=(3, 4), n=10):
     t0 = time.time()
     h = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0).hamilton_operator(nu, nd)
     tb = time.time() - t0
