@@ -356,7 +356,7 @@ def run_ours(args):
             "achieved_hbm_gbs_algorithmic": achieved * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "hub_row_kernel" if world == 1 else "sharded step (per GPU)",
+                         "kernel": "hub_seg_kernel" if world == 1 else "sharded step (per GPU)",
                          "algorithmic_bytes_per_launch": 16 * dim // world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
