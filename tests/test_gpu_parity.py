@@ -163,12 +163,12 @@ def test_hubbard_model_golden(cm, golden, name):
     hamop = model.hamilton_operator(nu, nd)
     x = np.cos(0.37 * np.arange(hamop.shape[0]))
     ref = golden[name + "_hv"]
-    for variant in (1, 2, 3, 0):
+    for variant in (1, 2, 3, 5, 6, 7, 0):
         try:
             hamop.set_variant(variant)
             y = hamop.matvec(x)
-        except Exception as exc:  # variants 2/3 need rows that fit shared memory
-            assert variant in (2, 3) and "variant" in str(exc), exc
+        except Exception as exc:  # variants 2/3/5-7 need complete sectors whose rows fit shared memory
+            assert variant in (2, 3, 5, 6, 7) and "variant" in str(exc), exc
             continue
         assert relerr(y, ref) < HV_RTOL
     hamop.set_variant(0)
@@ -233,7 +233,7 @@ def test_hv_l8_golden_both_kernels(cm, golden):
     model = HubbardModel(8, chain(8), inter=4.0, mu=2.0, hop=1.0)
     h = model.hamilton_operator(4, 4)
     x = np.cos(0.37 * np.arange(4900))
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 5, 6, 7):
         h.set_variant(variant)
         y = h.matvec(x)
         assert relerr(y, golden["hub_chain8_44_hv"]) < HV_RTOL
@@ -252,6 +252,11 @@ def test_hv_l8_golden_both_kernels(cm, golden):
     (9, 4, 5, lambda: orc.square_neighbors(3, 3), dict(inter=4.0, mu=2.0, hop=1.0)),
     (12, 6, 6, lambda: chain(12), dict(inter=4.0, mu=2.0, hop=1.0)),
     (12, 2, 9, lambda: orc.square_neighbors(4, 3), dict(inter=1.0, mu=0.2, hop=1.3)),
+    (11, 5, 3, lambda: chain(11, True), dict(inter=3.0, eps=-0.4, mu=0.5, hop=0.9)),
+    (13, 6, 7, lambda: chain(13), dict(inter=4.0, mu=2.0, hop=1.0)),
+    (12, 5, 7, lambda: orc.square_neighbors(3, 4), dict(inter=4.0, mu=2.0, hop=-1.0)),
+    (7, 3, 0, lambda: chain(7), dict(inter=4.0, mu=2.0, hop=1.0)),
+    (7, 4, 7, lambda: chain(7, True), dict(inter=4.0, mu=2.0, hop=1.0)),
 ])
 def test_hv_vs_oracle(cm, L, nu, nd, nbfn, kw):
     from cmpy_b200.models import HubbardModel
@@ -264,9 +269,41 @@ def test_hv_vs_oracle(cm, L, nu, nd, nbfn, kw):
     up, dn = orc.enumerate_states(L, nu), orc.enumerate_states(L, nd)
     ref = orc.hubbard_matvec_free(up, dn, nb, kw.get("inter", 0.0), kw.get("eps", 0.0) - kw.get("mu", 0.0),
                                   kw.get("hop", 1.0), x, width=L)
-    for variant in (1, 2, 3):
+    ran = []
+    for variant in (1, 2, 3, 5, 6, 7):
+        try:
+            h.set_variant(variant)
+            y = h.matvec(x)
+        except RuntimeError as exc:  # degenerate / odd-length rows have no class-major variant
+            assert "variant" in str(exc), exc
+            continue
+        ran.append(variant)
+        assert relerr(y, ref) < HV_RTOL, variant
+    from math import comb
+    assert 1 in ran and (5 in ran or comb(L, nd) % 2 == 1)
+    # accumulate / row-slab entry point used by the sharded operator (dn part only)
+    h.set_variant(0)
+
+
+def test_lanczos_fused_class_major_variants(cm):
+    """Fused Lanczos epilogue of the class-major kernel (variants 5-7) against the dense E0."""
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.exactdiag import lanczos_run
+
+    L, nb = 10, orc.square_neighbors(2, 5)
+    model = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0)
+    h = model.hamilton_operator(5, 5)
+    up = orc.enumerate_states(L, 5)
+    import scipy.sparse.linalg as sla
+    r, c, v = orc.hubbard_triplets(up, up, L, nb, 4.0, -2.0, 1.0)
+    import scipy.sparse as sp
+    a = sp.csr_matrix((v, (r, c)), shape=(h.shape[0],) * 2)
+    e_ref = sla.eigsh(a, k=1, which="SA", tol=0)[0][0]
+    for variant in (5, 6, 7, 3):
         h.set_variant(variant)
-        assert relerr(h.matvec(x), ref) < HV_RTOL
+        res = lanczos_run(h, None, maxit=400, tol=1e-12, resid_tol=1e-9)
+        assert abs(res.e0 - e_ref) < 1e-10, (variant, res.e0, e_ref)
+    h.set_variant(0)
 
 
 def test_hv_siam_vs_oracle(cm):
@@ -318,9 +355,11 @@ def test_hv_torch_zero_copy_and_properties_c4(cm):
     assert abs(lhs - rhs) < 1e-9 * max(abs(lhs), 1.0) * 10
     hxy = h.matvec(2.0 * x - 0.5 * y)
     assert float((hxy - (2.0 * hx - 0.5 * hy)).abs().max()) < 1e-11 * float(hx.abs().max())
-    h.set_variant(1)
-    hx1 = h.matvec(x)
-    assert float((hx1 - hx).abs().max()) < 1e-12 * float(hx.abs().max())
+    for variant in (1, 4, 5, 6, 7):
+        h.set_variant(variant)
+        hx1 = h.matvec(x)
+        assert float((hx1 - hx).abs().max()) < 1e-12 * float(hx.abs().max()), variant
+    h.set_variant(0)
     # spot rows against the oracle: restrict x to one up-row neighbourhood is not possible
     # matrix-free, so compare the diagonal instead
     d = h.diagonal()

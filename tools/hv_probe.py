@@ -13,7 +13,11 @@ cfg = {"c4": (16, orc.square_neighbors(4, 4), 8, 8), "c2": (12, orc.chain_neighb
 h = HubbardModel(cfg[0], cfg[1], inter=4.0, mu=2.0, hop=1.0).hamilton_operator(cfg[2], cfg[3])
 h.set_variant(variant)
 x = torch.randn(h.shape[0], dtype=torch.float64, device="cuda"); y = torch.empty_like(x)
+dn_only = len(sys.argv) > 4 and sys.argv[4] == "dn"
 for _ in range(n):
-    h.apply(x, out=y)
+    if dn_only:
+        h.apply_rows(x, 0, len(h.up_states), out=y)
+    else:
+        h.apply(x, out=y)
 torch.cuda.synchronize()
 print("done", which, variant, float(y[0]))

@@ -17,7 +17,7 @@ def timeit(fn, n=10, warm=3):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
-def run(name, L, nb, nu, nd, variants=(3, 4), n=10):
+def run(name, L, nb, nu, nd, variants=(3, 4, 5, 6, 7), n=10):
     t0 = time.time()
     h = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0).hamilton_operator(nu, nd)
     tb = time.time() - t0
@@ -31,6 +31,13 @@ def run(name, L, nb, nu, nd, variants=(3, 4), n=10):
             print(f"{name} dim={dim} variant={v}: {ms:.4f} ms  {16*dim/ms/1e6:.1f} GB/s algorithmic  (build {tb:.2f}s)", flush=True)
         except Exception as e:
             print(name, "variant", v, "failed:", e, flush=True)
+    for v in (4, 5, 6, 7):   # dn-only pass (row slab entry point, no up hops)
+        try:
+            h.set_variant(v)
+            ms = timeit(lambda: h.apply_rows(x, 0, len(h.up_states), out=y), n=n)
+            print(f"{name} dn-only variant={v}: {ms:.4f} ms  {16*dim/ms/1e6:.1f} GB/s algorithmic", flush=True)
+        except Exception as e:
+            print(name, "dn-only variant", v, "failed:", e, flush=True)
     h.set_variant(0)
     t0 = time.time()
     res = lanczos_run(h, None, maxit=400, tol=1e-10)
