@@ -9,6 +9,7 @@
 #include "lanczos.cuh"
 #include "greens.cuh"
 #include "heisenberg.cuh"
+#include "peer.cuh"
 
 #define API extern "C" __attribute__((visibility("default")))
 
@@ -399,6 +400,54 @@ API int cmpy_copy2d(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld
   if (nrows == 0 || ncols == 0) return CMPY_OK;
   copy2d_kernel<<<grid_for(nrows * ncols, 256, 148 * 16), 256, 0, as_stream(stream)>>>(
       d_in, nrows, ncols, ld_in, d_out, ld_out, accumulate);
+  KERNEL_CHECK();
+  return CMPY_OK;
+}
+
+// ---- K9 over peer memory -----------------------------------------------------------------
+static int fill_peer_table(PeerTable& pt, int world, const int64_t* h_col_bounds, void* const* h_peer_ptrs) {
+  ARG_CHECK(world >= 1 && world <= PEER_MAX, "peer transpose: 1 <= world <= 16");
+  ARG_CHECK(h_col_bounds && h_peer_ptrs, "peer transpose: null tables");
+  pt.world = world;
+  for (int q = 0; q < world; ++q) {
+    ARG_CHECK(h_peer_ptrs[q], "peer transpose: null peer pointer");
+    ARG_CHECK(h_col_bounds[q] <= h_col_bounds[q + 1], "peer transpose: column bounds must ascend");
+    pt.base[q] = (double*)h_peer_ptrs[q];
+    pt.cb[q] = h_col_bounds[q];
+  }
+  pt.cb[world] = h_col_bounds[world];
+  return CMPY_OK;
+}
+
+API int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                            int64_t ld_t, int world, const int64_t* h_col_bounds,
+                            void* const* h_peer_ptrs, void* stream) {
+  ARG_CHECK(d_x_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
+  PeerTable pt;
+  int rc = fill_peer_table(pt, world, h_col_bounds, h_peer_ptrs);
+  if (rc) return rc;
+  ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
+  if (nrows == 0 || num_dn == 0) return CMPY_OK;
+  const i64 ntiles = ((nrows + 31) / 32) * ((num_dn + 31) / 32);
+  const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  peer_transpose_kernel<false><<<g, 256, 0, as_stream(stream)>>>(const_cast<double*>(d_x_slab), nrows,
+                                                                 num_dn, row0, ld_t, pt);
+  KERNEL_CHECK();
+  return CMPY_OK;
+}
+
+API int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                                int64_t ld_t, int world, const int64_t* h_col_bounds,
+                                void* const* h_peer_ptrs, void* stream) {
+  ARG_CHECK(d_y_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
+  PeerTable pt;
+  int rc = fill_peer_table(pt, world, h_col_bounds, h_peer_ptrs);
+  if (rc) return rc;
+  ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
+  if (nrows == 0 || num_dn == 0) return CMPY_OK;
+  const i64 ntiles = ((nrows + 31) / 32) * ((num_dn + 31) / 32);
+  const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  peer_transpose_kernel<true><<<g, 256, 0, as_stream(stream)>>>(d_y_slab, nrows, num_dn, row0, ld_t, pt);
   KERNEL_CHECK();
   return CMPY_OK;
 }

@@ -14,6 +14,14 @@ layout, where they are again row-local:
   5. YT_local = T_up XT_local                              same local kernel, roles swapped
   6. pack / exchange / accumulate back into y_local        transpose + all-to-all + copy2d(+=)
 
+On CUDA with more than one rank the default exchange is ``"peer"``: the XT / YT slabs live in
+symmetric memory (``torch.distributed._symmetric_memory``), steps 2-4 are ONE kernel that reads
+the local slab and stores the transposed tiles straight into the owners' XT slabs over NVLink
+(``cmpy_transpose_push``), step 6 is ONE kernel that loads the peers' YT tiles over NVLink and
+accumulates them into y (``cmpy_transpose_pull_acc``); cross-rank barriers order the phases and
+the push runs on a side stream under the local dn pass.  No staging slabs: x, y, XT, YT only.
+``exchange="a2a"`` keeps the NCCL all-to-all choreography (also what the gloo CPU tests drive).
+
 Two transposes per H.v move 2 * 8 * dim * (P-1)/P bytes over NVLink.  The reference has no
 distributed path at all; results are checked against the single-GPU operator / the oracle.
 
@@ -111,7 +119,8 @@ class ShardedHubbardOperator:
     """H.v on the slab of up-rows owned by this rank; ``apply_local(x_local)`` returns
     ``(H x)_local``.  ``model`` is a ``HubbardModel`` / ``SingleImpurityAndersonModel``."""
 
-    def __init__(self, model, n_up, n_dn, group=None, backend=None, up_states=None, dn_states=None):
+    def __init__(self, model, n_up, n_dn, group=None, backend=None, up_states=None, dn_states=None,
+                 exchange=None):
         import torch.distributed as dist
 
         self.dist = dist
@@ -138,11 +147,66 @@ class ShardedHubbardOperator:
         size = self.plan.num_up * self.plan.num_dn
         self.shape = (size, size)
         p = self.plan
-        self._send = backend.empty(max(p.local_size, p.local_size_t))
-        self._recv = backend.empty(max(p.local_size, p.local_size_t))
-        self._xt = backend.empty(p.local_size_t)
-        self._yt = backend.empty(p.local_size_t)
+        if exchange is None:
+            exchange = "peer" if (isinstance(backend, CudaBackend) and self.world > 1) else "a2a"
+        if exchange not in ("peer", "a2a"):
+            raise ValueError("exchange must be 'peer' or 'a2a'")
+        self.exchange = exchange
+        if exchange == "peer":
+            self._init_peer()
+        else:
+            self._send = backend.empty(max(p.local_size, p.local_size_t))
+            self._recv = backend.empty(max(p.local_size, p.local_size_t))
+            self._xt = backend.empty(p.local_size_t)
+            self._yt = backend.empty(p.local_size_t)
         self._pinned_out = None
+
+    def _init_peer(self):
+        """XT / YT slabs in symmetric memory + the peer pointer tables of the transpose kernels."""
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        torch = _lib.require_cuda()
+        p = self.plan
+        group = self.group if self.group is not None else self.dist.group.WORLD
+        # symmetric allocations have the same size on every rank: the largest dn-major slab
+        n_t = max((p.cols(q)[1] - p.cols(q)[0]) for q in range(self.world)) * p.num_up
+        dev = _lib.device()
+        self._xt_sym = symm.empty(max(n_t, 1), dtype=torch.float64, device=dev)
+        self._yt_sym = symm.empty(max(n_t, 1), dtype=torch.float64, device=dev)
+        self._h_xt = symm.rendezvous(self._xt_sym, group)
+        self._h_yt = symm.rendezvous(self._yt_sym, group)
+        self._xt = self._xt_sym[: max(p.local_size_t, 1)]
+        self._yt = self._yt_sym[: max(p.local_size_t, 1)]
+        self._peer_xt = (ctypes.c_void_p * self.world)(*[int(a) for a in self._h_xt.buffer_ptrs])
+        self._peer_yt = (ctypes.c_void_p * self.world)(*[int(a) for a in self._h_yt.buffer_ptrs])
+        self._cb = (ctypes.c_int64 * (self.world + 1))(*p.col_bounds)
+        self._side = torch.cuda.Stream()
+
+    def _apply_local_peer(self, x_local, out):
+        torch = _lib.require_cuda()
+        p, be, L = self.plan, self.backend, _lib.lib()
+        r0, _ = p.rows()
+        c0, _ = p.cols()
+        nrows, ncols, nu, nd = p.nrows, p.ncols, p.num_up, p.num_dn
+        main = torch.cuda.current_stream()
+        # every rank is done with the XT / YT slabs of the previous call
+        self._h_xt.barrier(channel=0)
+        # push the transposed tiles into the owners' XT slabs (side stream) under the local
+        # diagonal + dn-hop pass (main stream)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            _lib.check(L.cmpy_transpose_push(_lib.ptr(x_local), nrows, nd, r0, nu, self.world, self._cb,
+                                             self._peer_xt, _lib.stream_ptr()), "cmpy_transpose_push")
+        be.apply_rows(x_local, r0, nrows, out)
+        main.wait_stream(self._side)
+        self._h_xt.barrier(channel=0)          # all pushes have landed
+        be.apply_rows_t(self._xt, c0, ncols, self._yt)   # up hops, row-local in the dn-major slab
+        self._h_yt.barrier(channel=0)          # every YT slab is complete
+        _lib.check(L.cmpy_transpose_pull_acc(_lib.ptr(out), nrows, nd, r0, nu, self.world, self._cb,
+                                             self._peer_yt, _lib.stream_ptr()), "cmpy_transpose_pull_acc")
+        return out
 
     @property
     def local_size(self):
@@ -163,6 +227,8 @@ class ShardedHubbardOperator:
         nrows, ncols, nu, nd = p.nrows, p.ncols, p.num_up, p.num_dn
         if out is None:
             out = be.empty(p.local_size)
+        if self.exchange == "peer":
+            return self._apply_local_peer(x_local, out)
         # 1. local phase: diagonal + dn hops
         be.apply_rows(x_local, r0, nrows, out)
         # 2. pack transposed blocks, one per peer

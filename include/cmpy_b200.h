@@ -187,6 +187,22 @@ int cmpy_transpose(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_
 int cmpy_copy2d(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
                 double* d_out, int64_t ld_out, int accumulate, void* stream);
 
+/* ---- K9 over NVLink peer memory (one process per GPU, slabs in symmetric memory) ----
+ * push: for the local slab of up-rows [row0, row0+nrows) (row-major nrows x num_dn) and every
+ *       rank q owning the dn-columns [col_bounds[q], col_bounds[q+1]):
+ *         XT_q[(c - col_bounds[q]) * ld_t + row0 + r] = x[r * num_dn + c]
+ *       XT_q = h_peer_ptrs[q], a device pointer of THIS process that maps rank q's dn-major slab
+ *       (remote stores over NVLink for q != rank).  ld_t = num_up.
+ * pull_acc: y[r * num_dn + c] += YT_q[(c - col_bounds[q]) * ld_t + row0 + r]  (remote loads).
+ * The caller orders the phases with cross-rank barriers (cmpy_b200/dist.py).  No reference
+ * counterpart: cmpy has no distributed path; layout cmpy/operators.py:33-90. */
+int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                        int64_t ld_t, int world, const int64_t* h_col_bounds,
+                        void* const* h_peer_ptrs, void* stream);
+int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                            int64_t ld_t, int world, const int64_t* h_col_bounds,
+                            void* const* h_peer_ptrs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
