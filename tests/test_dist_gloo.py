@@ -34,13 +34,16 @@ class OracleBackend:
     def empty(self, n):
         return torch.zeros(max(int(n), 1), dtype=torch.float64)
 
-    def apply_rows(self, x, row0, nrows, out):
+    def apply_rows(self, x, row0, nrows, out, accumulate=False):
         nd = len(self.dn)
         X = x[: nrows * nd].view(nrows, nd).numpy()
         ups = self.up[row0:row0 + nrows]
         docc = np.array([[int(a & b).bit_count() for b in self.dn] for a in ups])
         Y = (self.e_up[row0:row0 + nrows, None] + self.e_dn[None, :] + self.inter * docc) * X + X @ self.t_dn.T
-        out[: nrows * nd] = torch.from_numpy(Y.reshape(-1))
+        if accumulate:
+            out[: nrows * nd] += torch.from_numpy(Y.reshape(-1))
+        else:
+            out[: nrows * nd] = torch.from_numpy(Y.reshape(-1))
         return out
 
     def apply_rows_t(self, xt, col0, ncols, out):
@@ -89,6 +92,15 @@ def _worker(rank, world, port, L, nu, nd, ret):
         # second application reuses the buffers
         yl2 = op.apply_local(xl).numpy()[: (r1 - r0) * len(dn)]
         ok = err < 1e-13 and np.array_equal(yl, yl2)
+        # accumulate mode (two-vector Lanczos) and the sharded Lanczos driver
+        acc = torch.ones(op.local_size, dtype=torch.float64)
+        op.apply_local(xl, out=acc, accumulate=True)
+        ok = ok and np.abs(acc.numpy() - 1.0 - yl).max() < 1e-12
+        from cmpy_b200.dist import lanczos_sharded
+        e0, al, be_, nit, conv = lanczos_sharded(op, maxit=300, tol=1e-12, check_every=5)
+        r, c, v = orc.hubbard_triplets(up, dn, L, nb, 4.0, -2.0, 1.0)
+        e_ref = np.linalg.eigvalsh(orc.coo_dense(len(up) * len(dn), r, c, v))[0]
+        ok = ok and conv and abs(e0 - e_ref) < 1e-9
         t = torch.tensor([1.0 if ok else 0.0])
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
