@@ -306,6 +306,15 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
             dist.all_reduce(t, group=op.group)
         return t
 
+    def dot(a, b):  # cuBLAS dot is limited to 2^31-1 elements; a slab of the 20-site sector has 4.3e9
+        step = 1 << 30
+        if a.numel() <= step:
+            return torch.dot(a, b)
+        acc = torch.zeros((), dtype=a.dtype, device=a.device)
+        for i in range(0, a.numel(), step):
+            acc += torch.dot(a[i:i + step], b[i:i + step])
+        return acc
+
     n = op.local_size
     if v0_local is None:
         dev = op.backend.empty(1).device
@@ -315,7 +324,7 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
     else:
         v = v0_local.clone()
     w = torch.zeros_like(v)
-    v.div_(torch.sqrt(allsum(torch.dot(v, v))))
+    v.div_(torch.sqrt(allsum(dot(v, v))))
     alphas = torch.zeros(int(maxit), dtype=torch.float64, device=v.device)
     betas = torch.zeros(int(maxit), dtype=torch.float64, device=v.device)
     e_prev, e0, converged, nit = None, float("nan"), False, 0
@@ -323,9 +332,9 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
         if j > 0:
             w.mul_(-betas[j - 1])
         op.apply_local(v, out=w, accumulate=True)
-        a = allsum(torch.dot(v, w))
+        a = allsum(dot(v, w))
         w.addcmul_(v, a, value=-1.0)
-        b = torch.sqrt(allsum(torch.dot(w, w)))
+        b = torch.sqrt(allsum(dot(w, w)))
         alphas[j] = a
         betas[j] = b
         nit = j + 1
