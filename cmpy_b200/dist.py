@@ -223,6 +223,37 @@ class ShardedHubbardOperator:
                                     output_split_sizes=recv_counts, input_split_sizes=send_counts,
                                     group=self.group)
 
+    def profile_phases(self, x_local, out, reps=5):
+        """Per-phase device times (ms, CUDA events, phases serialised) of the peer-memory H.v:
+        dn pass, push transpose, up pass, pull transpose, barrier.  Diagnostic only."""
+        torch = _lib.require_cuda()
+        assert self.exchange == "peer"
+        p, be, L = self.plan, self.backend, _lib.lib()
+        r0, _ = p.rows(); c0, _ = p.cols()
+        nrows, ncols, nu, nd = p.nrows, p.ncols, p.num_up, p.num_dn
+
+        def timed(fn):
+            self._h_xt.barrier(channel=0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        res = {}
+        res["dn_pass"] = timed(lambda: be.apply_rows(x_local, r0, nrows, out))
+        res["push"] = timed(lambda: _lib.check(L.cmpy_transpose_push(
+            _lib.ptr(x_local), nrows, nd, r0, nu, self.world, self._cb, self._peer_xt, _lib.stream_ptr())))
+        res["up_pass"] = timed(lambda: be.apply_rows_t(self._xt, c0, ncols, self._yt))
+        res["pull"] = timed(lambda: _lib.check(L.cmpy_transpose_pull_acc(
+            _lib.ptr(out), nrows, nd, r0, nu, self.world, self._cb, self._peer_yt, _lib.stream_ptr())))
+        res["barrier"] = timed(lambda: self._h_xt.barrier(channel=0))
+        own = nrows * ncols
+        res["nvlink_bytes_per_transpose"] = 8 * (p.local_size - own)
+        return res
+
     def apply_local(self, x_local, out=None, accumulate=False):
         """``out = (H x)_local`` (``accumulate``: ``out += (H x)_local``, used by the two-vector
         Lanczos recurrence)."""

@@ -41,6 +41,12 @@ for L, nb, nu, nd in cases:
             print(f"L={L} ({nu},{nd}) dim={n} world={world} exchange={exchange}: max rel err {float(t):.2e}, "
                   f"{float(ms):.3f} ms per H.v", flush=True)
         assert float(t) < 1e-12
+        if exchange == "peer" and L >= 14:
+            ph = sh.profile_phases(xl, yl)
+            if rank == 0:
+                gb = ph["nvlink_bytes_per_transpose"] / 1e9
+                print("   phases (ms): " + ", ".join(f"{k} {v:.3f}" for k, v in ph.items() if k != "nvlink_bytes_per_transpose")
+                      + f" | NVLink out {gb:.3f} GB/transpose -> push {gb / ph['push'] * 1e3:.0f} GB/s, pull {gb / ph['pull'] * 1e3:.0f} GB/s", flush=True)
         del sh, yl
     del full, x, y
     torch.cuda.empty_cache()
