@@ -523,6 +523,24 @@ def gf_lehmann_finite_t(sector_solver, num_sites, z, beta, pos=0, sigma=UP):
 # helpers shared by tests / bench
 # ---------------------------------------------------------------------------
 
+def gf_realtime_dense(num_sites, neighbors, inter, eps, hop, n_up, n_dn, gs_energy, gs_state, times,
+                      pos=0, greater=True):
+    """`gf_greater` / `gf_lesser` (cmpy/exactdiag.py:248-301, sigma=UP) with a dense
+    eigendecomposition of the target-sector Hamiltonian in place of `expm_multiply`:
+    greater: -i e^{+i E0 t} <phi| e^{-i H t} |phi>, phi = c^+_pos |gs> (signless ladder);
+    lesser:  +i e^{-i E0 t} <phi| e^{+i H t} |phi>, phi = c_pos |gs>."""
+    up, dn = enumerate_states(num_sites, n_up), enumerate_states(num_sites, n_dn)
+    up_t = enumerate_states(num_sites, n_up + 1 if greater else n_up - 1)
+    phi = ladder_apply(np.asarray(gs_state, dtype=np.float64), up, dn, up_t, dn, pos, 1, bool(greater))
+    r, c, v = hubbard_triplets(up_t, dn, num_sites, neighbors, inter, eps, hop)
+    ev, vecs = np.linalg.eigh(coo_dense(len(up_t) * len(dn), r, c, v))
+    a2 = (vecs.T @ phi) ** 2
+    sgn = -1.0 if greater else 1.0
+    times = np.asarray(times, dtype=np.float64)
+    overlaps = (np.exp(1j * sgn * np.outer(times, ev)) * a2[None, :]).sum(axis=1)
+    return (1j * sgn) * np.exp(-1j * sgn * gs_energy * times) * overlaps
+
+
 def chain_neighbors(num_sites, periodic=False):
     nb = [[i, i + 1] for i in range(num_sites - 1)]
     if periodic and num_sites > 2:

@@ -4,6 +4,8 @@ the unmodified reference, and through size-independent properties at the BASELIN
 
 Bars: bit-exact for states / indices / signs / matrix elements; H.v 1e-12 relative;
 E0 1e-10; G(z) 1e-8 (BASELINE.json north_star)."""
+import os
+
 import numpy as np
 import pytest
 from numpy.testing import assert_array_equal, assert_allclose
@@ -738,3 +740,43 @@ def test_host_tensor_matvec(cm):
     y = h.matvec(x)
     assert not y.is_cuda
     assert float((y - h.matvec(x.cuda()).cpu()).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------
+# f-2: real-time Green's functions against the unmodified reference
+# (tests/golden/reference_tevo.npz, generated by oracle/make_golden_tevo.py)
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("L,pos", [(4, 0), (4, 2), (5, 0), (6, 0)])
+def test_gf_greater_lesser_golden(cm, L, pos):
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200 import exactdiag as ed
+    from cmpy_b200.matrix import EigenState
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_tevo.npz"))
+    key = f"L{L}_p{pos}"
+    model = HubbardModel(L, chain(L), inter=4.0, mu=2.0, hop=1.0)
+    n_up, n_dn = (int(v) for v in g[key + "_gs_sector"])
+    gs = EigenState(float(g[key + "_gs_energy"]), g[key + "_gs_state"], n_up, n_dn)
+    times = g[key + "_times"]
+    t, gg = ed.gf_greater(model, gs, times[0], times[-1], len(times), pos, cm.UP)
+    assert_allclose(t, times, atol=1e-14)
+    assert np.abs(gg - g[key + "_greater"]).max() < 1e-8      # G(t) to 1e-8, as for G(omega)
+    t, gl = ed.gf_lesser(model, gs, times[0], times[-1], len(times), pos, cm.UP)
+    assert np.abs(gl - g[key + "_lesser"]).max() < 1e-8
+    if L != 5:  # unique ground state: the sweep over sectors finds the same state
+        t, gt = ed.gf_tevo(model, times[0], times[-1], len(times), pos, cm.UP)
+        assert np.abs(gt - (g[key + "_greater"] - g[key + "_lesser"])).max() < 1e-7
+
+
+def test_fourier_t2z_analytic(cm):
+    """G(t) = -i exp(-i eps t)  ->  G(z) = 1/(z - eps) for Im z > 0 (piecewise-linear rule)."""
+    from cmpy_b200 import exactdiag as ed
+
+    eps = 0.7
+    t = np.linspace(0.0, 200.0, 40001)
+    gt = -1j * np.exp(-1j * eps * t)
+    om = np.linspace(-3, 3, 61)
+    z, gz = ed.fourier_t2z(t, gt, om, delta=1e-8)
+    ref = 1.0 / (z - eps)
+    assert np.abs(gz - ref).max() < 2e-5 * np.abs(ref).max()

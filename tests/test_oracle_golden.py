@@ -264,3 +264,18 @@ def test_reference_lanczos(golden):
     a2, b2, _ = orc.lanczos_coeffs_normalised(lambda q: ham @ q, golden["lanczos_ref_psi0"], 12)
     assert_allclose(a2, a, rtol=1e-9)
     assert_allclose(b2, b, rtol=1e-9)
+
+
+@pytest.mark.parametrize("L,pos", [(4, 0), (4, 2), (5, 0), (6, 0)])
+def test_realtime_gf_oracle_vs_reference(L, pos):
+    """Oracle restatement of gf_greater / gf_lesser against the unmodified reference's output
+    (tests/golden/reference_tevo.npz, oracle/make_golden_tevo.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_tevo.npz"))
+    key = f"L{L}_p{pos}"
+    nb = orc.chain_neighbors(L)
+    n_up, n_dn = (int(v) for v in g[key + "_gs_sector"])
+    for greater, name in ((True, "_greater"), (False, "_lesser")):
+        out = orc.gf_realtime_dense(L, nb, 4.0, -2.0, 1.0, n_up, n_dn, float(g[key + "_gs_energy"]),
+                                    g[key + "_gs_state"], g[key + "_times"], pos, greater)
+        assert np.abs(out - g[key + name]).max() < 1e-10
