@@ -428,10 +428,10 @@ API int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_d
   if (rc) return rc;
   ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
   if (nrows == 0 || num_dn == 0) return CMPY_OK;
-  const i64 ntiles = ((nrows + 31) / 32) * ((num_dn + 31) / 32);
+  const i64 ntiles = ((nrows + 127) / 128) * ((num_dn + 31) / 32);
   const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-  peer_transpose_kernel<false><<<g, 256, 0, as_stream(stream)>>>(const_cast<double*>(d_x_slab), nrows,
-                                                                 num_dn, row0, ld_t, pt);
+  peer_transpose_kernel<false, 128><<<g, 256, 0, as_stream(stream)>>>(const_cast<double*>(d_x_slab), nrows,
+                                                                      num_dn, row0, ld_t, pt);
   KERNEL_CHECK();
   return CMPY_OK;
 }
@@ -447,7 +447,7 @@ API int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn,
   if (nrows == 0 || num_dn == 0) return CMPY_OK;
   const i64 ntiles = ((nrows + 31) / 32) * ((num_dn + 31) / 32);
   const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-  peer_transpose_kernel<true><<<g, 256, 0, as_stream(stream)>>>(d_y_slab, nrows, num_dn, row0, ld_t, pt);
+  peer_transpose_kernel<true, 32><<<g, 256, 0, as_stream(stream)>>>(d_y_slab, nrows, num_dn, row0, ld_t, pt);
   KERNEL_CHECK();
   return CMPY_OK;
 }

@@ -780,3 +780,27 @@ def test_fourier_t2z_analytic(cm):
     z, gz = ed.fourier_t2z(t, gt, om, delta=1e-8)
     ref = 1.0 / (z - eps)
     assert np.abs(gz - ref).max() < 2e-5 * np.abs(ref).max()
+
+
+def test_matvec_batch_pipelined_host_vectors(cm):
+    """Pipelined host batch (three streams, double buffering) == one blocking matvec per vector."""
+    import torch
+    from cmpy_b200.models import HubbardModel
+
+    model = HubbardModel(12, chain(12), inter=4.0, mu=2.0, hop=1.0)
+    h = model.hamilton_operator(6, 6)
+    n = h.shape[0]
+    rng = np.random.default_rng(3)
+    xs = [torch.from_numpy(rng.standard_normal(n)).pin_memory() for _ in range(5)]
+    outs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(5)]
+    res = h.matvec_batch(xs, outs)
+    assert len(res) == 5
+    for x, y in zip(xs, res):
+        ref = h.matvec(x.numpy())
+        assert relerr(y.numpy(), ref) < HV_RTOL
+    # default output buffers: the last two results stay valid
+    res = h.matvec_batch(xs)
+    assert relerr(res[-1].numpy(), h.matvec(xs[-1].numpy())) < HV_RTOL
+    assert relerr(res[-2].numpy(), h.matvec(xs[-2].numpy())) < HV_RTOL
+    with pytest.raises(TypeError):
+        h.matvec_batch([torch.zeros(3, dtype=torch.float64)])
