@@ -172,6 +172,8 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
     rc = op->configure_seg(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (!rc && fixed_popcount)
     rc = op->configure_cls(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
+  if (!rc && fixed_popcount)
+    rc = op->configure_long(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (rc) { delete op; return rc; }
   *out = op;
   return CMPY_OK;
@@ -256,7 +258,7 @@ API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_
 }
 
 API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
-  ARG_CHECK(op && variant >= 0 && variant <= 7, "bad variant");
+  ARG_CHECK(op && variant >= 0 && variant <= 8, "bad variant");
   op->variant = variant;
   return CMPY_OK;
 }

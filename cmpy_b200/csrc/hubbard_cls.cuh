@@ -43,7 +43,7 @@ struct ClsLayout {
   int off_k_of_q;    // u8  [nq]
   int off_dl_of_q;   // u16 [nq]   bit pattern of dl
   int off_ll_ptr;    // u32 [nq]   start | (# '+' pairs) << 16 | (# pairs) << 24
-  int off_ll_ent;    // u16 [..]   r'; '+' entries first; both parts padded to pairs with S_k
+  int off_ll_ent;    // u8  [..]   r'; '+' entries first; both parts padded to pairs with S_k
   int off_dh_list;   // u16 [nseg] class-major list of dh
   int off_hi_goff;   // u16 [nhi]  offset of the segment inside a row (global layout)
   int off_hi_sbase;  // u16 [nhi]  offset of the segment inside xs
@@ -51,14 +51,35 @@ struct ClsLayout {
   int off_hh_ptr;    // u32 [nhi]  start | (# '+' pairs) << 16 | (# pairs) << 24
   int off_hh_ent;    // u16 [..]   sbase of the source segment; padded with the zero region
   int off_lh_hi;     // u16 [nlh][nhi]     sbase of segment dh^bit | par << 14 | bit << 15
-  int off_lh_lo;     // u16 [nlh][2][nq]   per value of the dh bit: r' | par << 15, or the slack slot
+  int off_lh_lo;     // u8  [nlh][2][nq]   per value of the dh bit: r' | par << 7, or the slack slot
   int off_seg_delta; // i16 [nseg + 1]     (sbase - goff) of the segments in natural order
   int bytes;
+};
+
+// Long rows (more than 16 sites): the dn string is (dtop, drest), drest = low 16 bits.  For a
+// fixed dtop the strings are contiguous in the row (a "sub-row" of C(16, n_dn - popc(dtop))
+// amplitudes) and the class-major machinery runs on the sub-row as if it were a 16-site row.
+// Bonds inside dtop map a sub-row onto a sub-row of the same length (handled like up hops:
+// coalesced 16-byte gathers in phase C); bonds with one site on each side change the sub-row
+// AND the rank (index map from global memory, per-lane gathers in phase C).  One launch per
+// popcount of dtop (the tables depend on it).
+struct LongCtx {
+  int ntop;                 // sub-rows per up-row in this launch
+  int row_len;              // amplitudes per sub-row
+  int nsb;                  // bonds straddling site 15|16
+  const uint32_t* top_val;  // [ntop]     dtop
+  const int* sub_off;       // [ntop]     offset of the sub-row inside the dn row
+  const int* tb_ptr;        // [ntop + 1] top-bond hop lists
+  const int2* tb_ent;       //            (offset relative to this sub-row, 1 = negative)
+  const int2* sb_src;       // [nsb][ntop] (relative offset of the source sub-row, flags: bit0 valid,
+                            //             bit1 = dtop bit set, bit2 = parity of the dtop part)
+  const uint32_t* sb_map;   // [nsb][2][row_len] rank in the source sub-row | parity << 30 | valid << 31
 };
 
 struct ClsParams {
   HubParams hp;
   ClsLayout lay;
+  LongCtx lg;
   const unsigned char* blob;
   const uint16_t* pair_seg;  // global: natural segment ordinal of column 2*i | straddle << 15
   double e_dn_const;
@@ -74,7 +95,7 @@ struct __align__(16) UpEnt2 { int off; int pad; double coef; };  // element offs
 // ---- phase A body: one (k, r) pair, T blocks of 32 dh-segments (lanes along jj) ----
 template <int T>
 __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const double* __restrict__ xs,
-                                            double* __restrict__ ys, const uint16_t* __restrict__ ll_ent,
+                                            double* __restrict__ ys, const uint8_t* __restrict__ ll_ent,
                                             const uint16_t* __restrict__ dh_list, uint32_t pp, int k,
                                             int r, uint32_t dlbits, uint32_t ups, double eu, double u0,
                                             double hop0, int lane) {
@@ -85,22 +106,22 @@ __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const double* __
   double ap[T], an[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
-  const uint32_t* ent2 = reinterpret_cast<const uint32_t*>(ll_ent + (pp & 0xffffu));
+  const uint16_t* ent2 = reinterpret_cast<const uint16_t*>(ll_ent + (pp & 0xffffu));
   const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
   int i = 0;
 #pragma unroll 1
   for (; i < npos; ++i) {
     const uint32_t e = ent2[i];
-    const double* __restrict__ q0 = xs + (e & 0xffffu);
-    const double* __restrict__ q1 = xs + (e >> 16);
+    const double* __restrict__ q0 = xs + (e & 0xffu);
+    const double* __restrict__ q1 = xs + (e >> 8);
 #pragma unroll
     for (int t = 0; t < T; ++t) { ap[t] += q0[o[t]]; an[t] -= q1[o[t]]; }
   }
 #pragma unroll 1
   for (; i < ntot; ++i) {
     const uint32_t e = ent2[i];
-    const double* __restrict__ q0 = xs + (e & 0xffffu);
-    const double* __restrict__ q1 = xs + (e >> 16);
+    const double* __restrict__ q0 = xs + (e & 0xffu);
+    const double* __restrict__ q1 = xs + (e >> 8);
 #pragma unroll
     for (int t = 0; t < T; ++t) { an[t] += q0[o[t]]; ap[t] -= q1[o[t]]; }
   }
@@ -121,7 +142,7 @@ template <int T>
 __device__ __forceinline__ void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
                                             double* __restrict__ ys, const uint16_t* __restrict__ hh_ent,
                                             const uint16_t* __restrict__ lh_hi,
-                                            const uint16_t* __restrict__ lh_lo, uint32_t pp, int k,
+                                            const uint8_t* __restrict__ lh_lo, uint32_t pp, int k,
                                             int dh, int sb, double hop0, int lane) {
   const int sk = L.S[k];
   const double* __restrict__ xp0 = xs + lane;
@@ -147,19 +168,19 @@ __device__ __forceinline__ void cls_phase_b(const ClsLayout& L, const double* __
 #pragma unroll
     for (int t = 0; t < T; ++t) { hn[t] += q0[32 * t]; hp[t] -= q1[32 * t]; }
   }
-  const uint16_t* __restrict__ lo0 = lh_lo + L.qoff[k] + lane;
+  const uint8_t* __restrict__ lo0 = lh_lo + L.qoff[k] + lane;
 #pragma unroll 1
   for (int b = 0; b < L.nlh; ++b) {
     const uint32_t hi = lh_hi[b * L.nhi + dh];
     const double* __restrict__ xh = xs + (hi & 0x3fffu);
-    const uint16_t* __restrict__ lo_tab = lo0 + (2 * b + (int)(hi >> 15)) * L.nq;
+    const uint8_t* __restrict__ lo_tab = lo0 + (2 * b + (int)(hi >> 15)) * L.nq;
     const uint32_t par_hi = (hi >> 14) << 31;  // bit 14 of hi -> sign bit position
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       // table rows are nq long and r < 96 <= slack after the last class: in bounds for every lane
       const uint32_t lo = lo_tab[32 * t];
-      const double v = xh[lo & 0x7fffu];
-      const int vh = __double2hiint(v) ^ (int)(((lo << 16) ^ par_hi) & 0x80000000u);
+      const double v = xh[lo & 0x7fu];
+      const int vh = __double2hiint(v) ^ (int)(((lo << 24) ^ par_hi) & 0x80000000u);
       hp[t] += __hiloint2double(vh, __double2loint(v));
     }
   }
@@ -175,7 +196,7 @@ __device__ __forceinline__ int seg_delta_g(const ClsParams& cp, int si) {
 
 // smem: [table blob][xs: xs_elems + CLS_ZREG doubles][ys: xs_elems doubles]
 // UPG = 0 compiles the up-hop gathers out (row-slab launches of the sharded operator).
-template <bool LZ, int NT, int UPG_>
+template <bool LZ, int NT, int UPG_, bool LONG = false>
 __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   constexpr bool WITH_UP = UPG_ > 0;
   constexpr int UPG = WITH_UP ? UPG_ : 1;
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   const HubParams& p = cp.hp;
   const ClsLayout& L = cp.lay;
   const i64 nd = p.num_dn, nu = p.num_up;
-  const int ndi = (int)nd;
+  const int ndi = LONG ? cp.lg.row_len : (int)nd;   // amplitudes handled per work item
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = NT / 32;
   unsigned char* tab = smem_raw;
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   const uint8_t* k_of_q = tab + L.off_k_of_q;
   const uint16_t* dl_of_q = reinterpret_cast<const uint16_t*>(tab + L.off_dl_of_q);
   const uint32_t* ll_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_ll_ptr);
-  const uint16_t* ll_ent = reinterpret_cast<const uint16_t*>(tab + L.off_ll_ent);
+  const uint8_t* ll_ent = tab + L.off_ll_ent;
   const uint16_t* dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list);
   const uint16_t* hi_goff = reinterpret_cast<const uint16_t*>(tab + L.off_hi_goff);
   const uint16_t* hi_sbase = reinterpret_cast<const uint16_t*>(tab + L.off_hi_sbase);
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   const uint32_t* hh_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ptr);
   const uint16_t* hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
   const uint16_t* lh_hi = reinterpret_cast<const uint16_t*>(tab + L.off_lh_hi);
-  const uint16_t* lh_lo = reinterpret_cast<const uint16_t*>(tab + L.off_lh_lo);
+  const uint8_t* lh_lo = tab + L.off_lh_lo;
 
   int j; double s1, s2; bool has_prev;
   lz_scalars<LZ>(p.lz, j, s1, s2, has_prev);
@@ -244,10 +265,15 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
 #else
 #define CLS_TICK(i)
 #endif
-  for (i64 r_row = blockIdx.x; r_row < p.nrows; r_row += gridDim.x) {
+  const i64 nitems = LONG ? p.nrows * cp.lg.ntop : p.nrows;
+  for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const i64 r_row = LONG ? item / cp.lg.ntop : item;
+    const int ti = LONG ? (int)(item - r_row * cp.lg.ntop) : 0;
     const i64 u = p.row0 + r_row;
-    const double* __restrict__ xr = p.x + r_row * nd;
-    double* __restrict__ yr = p.y + r_row * nd;
+    const i64 base = r_row * nd + (LONG ? (i64)cp.lg.sub_off[ti] : 0);
+    const double* __restrict__ xr = p.x + base;
+    double* __restrict__ yr = p.y + base;
+    const uint32_t dtop = LONG ? cp.lg.top_val[ti] : 0u;
     __syncthreads();  // previous row fully consumed (first pass: tables loaded, xs zeroed)
     CLS_TICK(0)
     // ---- stage the row: natural order -> class-major padded layout ----
@@ -258,24 +284,31 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
       double* __restrict__ dst = xs + hi_sbase[dh];
       for (int r = lane; r < sk; r += 32) dst[r] = __ldg(src + r);
     }
-    const int cu = (WITH_UP && p.with_up) ? (int)p.cnt_up[u] : 0;
+    const int tb0 = LONG ? cp.lg.tb_ptr[ti] : 0;
+    const int cu = LONG ? cp.lg.tb_ptr[ti + 1] - tb0 : ((WITH_UP && p.with_up) ? (int)p.cnt_up[u] : 0);
     if (WITH_UP && tid < ELL_MAX_BONDS + 32) {
       UpEnt2 ue;
       ue.off = 0; ue.pad = 0; ue.coef = 0.0;  // padding: never loaded, coefficient 0
       if (tid < cu) {
-        const uint32_t e = p.ell_up[(i64)tid * nu + u];
-        ue.off = (int)(((i64)(e & ELL_TGT_MASK) - u) * nd);  // relative to the current row
-        ue.coef = (e >> 31) ? -hop0 : hop0;
+        if (LONG) {  // hops inside dtop: whole sub-row onto a sub-row of the same up-row
+          const int2 e = cp.lg.tb_ent[tb0 + tid];
+          ue.off = e.x;
+          ue.coef = e.y ? -hop0 : hop0;
+        } else {
+          const uint32_t e = p.ell_up[(i64)tid * nu + u];
+          ue.off = (int)(((i64)(e & ELL_TGT_MASK) - u) * nd);  // relative to the current row
+          ue.coef = (e >> 31) ? -hop0 : hop0;
+        }
       }
       s_up[tid] = ue;
     }
     const uint32_t ups = p.up_states[u];
-    const double eu = p.e_up[u] + ediag0;
+    const double eu = p.e_up[u] + ediag0 + (LONG ? u0 * (double)__popc((ups >> 16) & dtop) : 0.0);
     CLS_TICK(1)
     __syncthreads();
     CLS_TICK(2)
 
-    if (r_row + gridDim.x < p.nrows) {  // pull the next row of this CTA into L2 while we compute
+    if (!LONG && r_row + gridDim.x < p.nrows) {  // pull the next row of this CTA into L2 while we compute
       const char* nxt = reinterpret_cast<const char*>(xr + (i64)gridDim.x * nd);
       for (int b = tid * 128; b < ndi * 8; b += NT * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + b));
@@ -344,6 +377,20 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
         }
       } else {
         a0 = ys[slot0]; a1 = ys[slot1];
+      }
+      if (LONG) {
+#pragma unroll 1
+        for (int sb = 0; sb < cp.lg.nsb; ++sb) {
+          const int2 src = cp.lg.sb_src[sb * cp.lg.ntop + ti];
+          if (src.y & 1) {
+            const uint32_t* map = cp.lg.sb_map + ((size_t)(2 * sb + ((src.y >> 1) & 1)) * ndi + d);
+            const uint2 e = *reinterpret_cast<const uint2*>(map);
+            const uint32_t ptop = (uint32_t)(src.y >> 2) & 1u;
+            const double* __restrict__ xsrc = xr + src.x;
+            if (e.x >> 31) a0 += flip_sign(hop0 * __ldg(xsrc + (e.x & 0x3fffffffu)), ((e.x >> 30) & 1u) ^ ptop);
+            if (e.y >> 31) a1 += flip_sign(hop0 * __ldg(xsrc + (e.y & 0x3fffffffu)), ((e.y >> 30) & 1u) ^ ptop);
+          }
+        }
       }
       double2* yp = reinterpret_cast<double2*>(yr + d);
       if (LZ) {
@@ -466,18 +513,20 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   };
   // pack a ('+' list, '-' list) into pairs, each part padded to an even length with `dummy`
   auto pack = [&](const std::vector<uint16_t>& pos, const std::vector<uint16_t>& neg, uint16_t dummy,
-                  std::vector<uint16_t>& out, uint32_t& ptr) -> bool {
+                  auto& out, uint32_t& ptr) -> bool {
     if (out.size() & 1) out.push_back(dummy);
     const size_t start = out.size();
     const size_t np2 = (pos.size() + 1) / 2, nn2 = (neg.size() + 1) / 2;
     if (start >= 65536 || np2 + nn2 > 255) return false;
-    for (size_t i = 0; i < 2 * np2; ++i) out.push_back(i < pos.size() ? pos[i] : dummy);
-    for (size_t i = 0; i < 2 * nn2; ++i) out.push_back(i < neg.size() ? neg[i] : dummy);
+    typedef typename std::remove_reference<decltype(out)>::type::value_type E;
+    for (size_t i = 0; i < 2 * np2; ++i) out.push_back((E)(i < pos.size() ? pos[i] : dummy));
+    for (size_t i = 0; i < 2 * nn2; ++i) out.push_back((E)(i < neg.size() ? neg[i] : dummy));
     ptr = (uint32_t)start | ((uint32_t)np2 << 16) | ((uint32_t)(np2 + nn2) << 24);
     return true;
   };
   std::vector<uint32_t> ll_ptr(nlo, 0), hh_ptr(nhi, 0);
-  std::vector<uint16_t> ll_ent, hh_ent;
+  std::vector<uint8_t> ll_ent;   // ranks and the slack slot are <= 96
+  std::vector<uint16_t> hh_ent;
   for (int q = 0; q < nlo; ++q) {
     const int dl = dl_of_q[q], k = k_of_q[q];
     std::vector<uint16_t> pos, negl;
@@ -503,7 +552,8 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
     if (!pack(pos, negl, (uint16_t)zbase, hh_ent, hh_ptr[dh])) return CMPY_OK;
   }
   // LH tables
-  std::vector<uint16_t> lh_hi((size_t)std::max(1, L.nlh) * nhi, 0), lh_lo((size_t)std::max(1, L.nlh) * 2 * nlo + 96, 0);  // + slack for lanes past a segment
+  std::vector<uint16_t> lh_hi((size_t)std::max(1, L.nlh) * nhi, 0);
+  std::vector<uint8_t> lh_lo((size_t)std::max(1, L.nlh) * 2 * nlo + 96, 0);  // + slack for lanes past a segment
   for (int qb = 0; qb < L.nlh; ++qb) {
     const int b = lh[qb];
     const int a = s1[b], c = s2[b] - m;  // a inside dl, c inside dh
@@ -519,15 +569,15 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
         const int dl = dl_of_q[q], k = k_of_q[q];
         const int bit_lo = (dl >> a) & 1;
         const int kp = k + (beta ? 1 : -1);  // class of the source segment
-        uint16_t e;
+        uint8_t e;
         if (kp < 0 || kp > m || L.H[kp] == 0) {
           e = 0;  // the hi entry points at the zero region
         } else if (bit_lo == beta) {
-          e = (uint16_t)L.S[kp];  // not allowed: slack slot of the source segment (0.0)
+          e = (uint8_t)L.S[kp];  // not allowed: slack slot of the source segment (0.0)
         } else {
           const int nl = dl ^ (1 << a);
           const int par = parity((u64)dl, a, m);  // bits of dl strictly above a
-          e = (uint16_t)(lo_rank[nl] | (par << 15));
+          e = (uint8_t)(lo_rank[nl] | (par << 7));
         }
         lh_lo[((size_t)qb * 2 + beta) * nlo + q] = e;
       }
@@ -552,7 +602,7 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   place(L.off_k_of_q, nlo);
   place(L.off_dl_of_q, 2 * nlo);
   place(L.off_ll_ptr, 4 * nlo);
-  place(L.off_ll_ent, 2 * ll_ent.size());
+  place(L.off_ll_ent, ll_ent.size());
   place(L.off_dh_list, 2 * dh_list.size());
   place(L.off_hi_goff, 2 * nhi);
   place(L.off_hi_sbase, 2 * nhi);
@@ -560,7 +610,7 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   place(L.off_hh_ptr, 4 * nhi);
   place(L.off_hh_ent, 2 * hh_ent.size());
   place(L.off_lh_hi, 2 * lh_hi.size());
-  place(L.off_lh_lo, 2 * lh_lo.size());
+  place(L.off_lh_lo, lh_lo.size());
   place(L.off_seg_delta, 2 * seg_delta.size());
   L.bytes = o;
   const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
@@ -575,7 +625,7 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   { auto t = narrow8(k_of_q); put(L.off_k_of_q, t.data(), t.size()); }
   { auto t = narrow16(dl_of_q); put(L.off_dl_of_q, t.data(), 2 * t.size()); }
   put(L.off_ll_ptr, ll_ptr.data(), 4 * ll_ptr.size());
-  put(L.off_ll_ent, ll_ent.data(), 2 * ll_ent.size());
+  put(L.off_ll_ent, ll_ent.data(), ll_ent.size());
   { auto t = narrow16(dh_list); put(L.off_dh_list, t.data(), 2 * t.size()); }
   { auto t = narrow16(hi_goff); put(L.off_hi_goff, t.data(), 2 * t.size()); }
   { auto t = narrow16(hi_sbase); put(L.off_hi_sbase, t.data(), 2 * t.size()); }
@@ -583,12 +633,168 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   put(L.off_hh_ptr, hh_ptr.data(), 4 * hh_ptr.size());
   put(L.off_hh_ent, hh_ent.data(), 2 * hh_ent.size());
   put(L.off_lh_hi, lh_hi.data(), 2 * lh_hi.size());
-  put(L.off_lh_lo, lh_lo.data(), 2 * lh_lo.size());
+  put(L.off_lh_lo, lh_lo.data(), lh_lo.size());
   { std::vector<int16_t> t(seg_delta.size()); for (size_t i = 0; i < t.size(); ++i) t[i] = (int16_t)seg_delta[i]; put(L.off_seg_delta, t.data(), 2 * t.size()); }
   CU_CHECK(cudaMalloc(&T.d_blob, o));
   CU_CHECK(cudaMemcpy(T.d_blob, blob.data(), o, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMalloc(&T.d_pair_seg, sizeof(uint16_t) * std::max<size_t>(pair_seg.size(), 1)));
   CU_CHECK(cudaMemcpy(T.d_pair_seg, pair_seg.data(), sizeof(uint16_t) * pair_seg.size(), cudaMemcpyHostToDevice));
   T.ok = true;
+  return CMPY_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// host: long rows (more than 16 sites), see LongCtx
+// ---------------------------------------------------------------------------------
+#define LONG_RBITS 16
+
+struct LongSet {            // all sub-rows whose dtop has the same popcount
+  ClsTables cls;            // class-major tables of the 16-site sub-row sector
+  int pt = 0, ntop = 0, row_len = 0;
+  uint32_t* d_top_val = nullptr;
+  int* d_sub_off = nullptr;
+  int* d_tb_ptr = nullptr;
+  int2* d_tb_ent = nullptr;
+  int2* d_sb_src = nullptr;
+  uint32_t* d_sb_map = nullptr;
+  void release() {
+    cls.release();
+    cudaFree(d_top_val); cudaFree(d_sub_off); cudaFree(d_tb_ptr); cudaFree(d_tb_ent);
+    cudaFree(d_sb_src); cudaFree(d_sb_map);
+    d_top_val = nullptr; d_sub_off = nullptr; d_tb_ptr = nullptr; d_tb_ent = nullptr;
+    d_sb_src = nullptr; d_sb_map = nullptr;
+  }
+};
+
+struct LongTables {
+  std::vector<LongSet> sets;
+  bool ok = false;
+  int nsb = 0;
+  double e_dn_const = 0.0;
+  void release() { for (auto& s : sets) s.release(); sets.clear(); ok = false; }
+};
+
+template <typename T>
+static int upload_vec(T*& dptr, const std::vector<T>& v) {
+  CU_CHECK(cudaMalloc(&dptr, sizeof(T) * std::max<size_t>(v.size(), 1)));
+  if (!v.empty()) CU_CHECK(cudaMemcpy(dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return CMPY_OK;
+}
+
+static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
+                             const int* s1, const int* s2, int sign_width, const double* eps,
+                             i64 smem_optin) {
+  T.release();
+  const u64* B = host_binom();
+  const int R = LONG_RBITS, tb = num_sites - R;
+  if (tb < 1 || tb > 12 || n_dn < 0 || n_dn > num_sites) return CMPY_OK;
+  if ((i64)B[num_sites * BINOM_N + n_dn] != num_dn || num_dn >= (1ll << 31)) return CMPY_OK;
+  const int ntopall = 1 << tb;
+  // sub-row offsets in the ascending (natural) order of the dn strings
+  std::vector<i64> sub_off(ntopall, -1);
+  {
+    i64 off = 0;
+    for (int dt = 0; dt < ntopall; ++dt) {
+      const int nr = n_dn - __builtin_popcount(dt);
+      if (nr < 0 || nr > R) continue;
+      sub_off[dt] = off;
+      off += (i64)B[R * BINOM_N + nr];
+    }
+    if (off != num_dn) return cmpy_fail(CMPY_ERR_ARG, "long tables: size mismatch");
+  }
+  std::vector<int> lo1, lo2, top, strad;
+  for (int b = 0; b < nbonds; ++b) {
+    if (s2[b] < R) { lo1.push_back(s1[b]); lo2.push_back(s2[b]); }
+    else if (s1[b] >= R) top.push_back(b);
+    else strad.push_back(b);
+  }
+  T.nsb = (int)strad.size();
+  auto parity = [&](u64 state, int a, int b2) {
+    return __builtin_popcountll(state & between_mask(a, b2, sign_width)) & 1;
+  };
+  { double v = 0; for (int i = 0; i < n_dn; ++i) v += eps[0]; T.e_dn_const = v; }
+  for (int pt = 0; pt <= tb; ++pt) {
+    const int nr = n_dn - pt;
+    if (nr < 0 || nr > R) continue;
+    LongSet S;
+    S.pt = pt;
+    S.row_len = (int)B[R * BINOM_N + nr];
+    int rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
+                              eps, smem_optin);
+    if (rc) { S.release(); return rc; }
+    if (!S.cls.ok) { S.release(); T.release(); return CMPY_OK; }
+    std::vector<uint32_t> top_val;
+    for (int dt = 0; dt < ntopall; ++dt)
+      if (__builtin_popcount(dt) == pt) top_val.push_back((uint32_t)dt);
+    S.ntop = (int)top_val.size();
+    std::vector<int> so(S.ntop), tb_ptr(S.ntop + 1, 0);
+    std::vector<int2> tb_ent, sb_src((size_t)std::max(1, T.nsb) * S.ntop, make_int2(0, 0));
+    for (int ti = 0; ti < S.ntop; ++ti) {
+      const int dt = (int)top_val[ti];
+      so[ti] = (int)sub_off[dt];
+      tb_ptr[ti] = (int)tb_ent.size();
+      for (int b : top) {
+        const int a = s1[b] - R, c = s2[b] - R;
+        if (((dt >> a) & 1) == ((dt >> c) & 1)) continue;
+        const int nt = dt ^ (1 << a) ^ (1 << c);
+        const int neg = parity((u64)dt << R, s1[b], s2[b]);
+        tb_ent.push_back(make_int2((int)(sub_off[nt] - sub_off[dt]), neg));
+      }
+      if ((int)tb_ent.size() - tb_ptr[ti] > ELL_MAX_BONDS) { S.release(); T.release(); return CMPY_OK; }
+      for (int q = 0; q < T.nsb; ++q) {
+        const int b = strad[q];
+        const int c = s2[b] - R;
+        const int bit = (dt >> c) & 1;
+        const int nt = dt ^ (1 << c);
+        const int nrs = nr + (bit ? 1 : -1);
+        int flags = 0, rel = 0;
+        if (nrs >= 0 && nrs <= R && sub_off[nt] >= 0) {
+          const int ptop = parity((u64)dt << R, R - 1, s2[b]);  // dtop bits strictly below c
+          flags = 1 | (bit << 1) | (ptop << 2);
+          rel = (int)(sub_off[nt] - sub_off[dt]);
+        }
+        sb_src[(size_t)q * S.ntop + ti] = make_int2(rel, flags);
+      }
+    }
+    tb_ptr[S.ntop] = (int)tb_ent.size();
+    // index maps of the straddling bonds for this n_rest (both directions)
+    std::vector<uint32_t> sb_map((size_t)std::max(1, T.nsb) * 2 * S.row_len, 0);
+    if (T.nsb > 0) {
+      std::vector<uint32_t> strings;
+      for (uint32_t v = 0; v < (1u << R); ++v)
+        if (__builtin_popcount(v) == nr) strings.push_back(v);
+      auto rank = [&](uint32_t v) {
+        i64 r = 0; int k = 0;
+        while (v) { const int pos = __builtin_ctz(v); v &= v - 1; ++k; r += (i64)B[pos * BINOM_N + k]; }
+        return (uint32_t)r;
+      };
+      for (int q = 0; q < T.nsb; ++q) {
+        const int a = s1[strad[q]];
+        for (int dir = 0; dir < 2; ++dir)
+          for (int r = 0; r < S.row_len; ++r) {
+            const uint32_t v = strings[r];
+            const int bit_a = (v >> a) & 1;
+            uint32_t e = 0;
+            // dir = 1: the dtop bit is set, the particle comes from dtop into site a (must be empty);
+            // dir = 0: the particle leaves site a (must be occupied) towards dtop
+            if (bit_a != dir) {
+              const uint32_t nv = v ^ (1u << a);
+              const uint32_t par = (uint32_t)parity((u64)v, a, R);  // drest bits strictly above a
+              e = rank(nv) | (par << 30) | (1u << 31);
+            }
+            sb_map[((size_t)q * 2 + dir) * S.row_len + r] = e;
+          }
+      }
+    }
+    rc = upload_vec(S.d_top_val, top_val);
+    if (!rc) rc = upload_vec(S.d_sub_off, so);
+    if (!rc) rc = upload_vec(S.d_tb_ptr, tb_ptr);
+    if (!rc) rc = upload_vec(S.d_tb_ent, tb_ent);
+    if (!rc) rc = upload_vec(S.d_sb_src, sb_src);
+    if (!rc) rc = upload_vec(S.d_sb_map, sb_map);
+    if (rc) { S.release(); T.release(); return rc; }
+    T.sets.push_back(S);
+  }
+  T.ok = !T.sets.empty();
   return CMPY_OK;
 }

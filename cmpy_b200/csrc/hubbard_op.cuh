@@ -40,13 +40,14 @@ struct HubbardOp : cmpy_op_s {
   int seg_threads = 256;
   int seg_blocks_per_sm = 1;
   bool seg_wide = false;     // 1024-thread CTAs (one CTA per SM, long rows)
+  LongTables lng;            // rows of more than 16 sites: sub-row launches of the class-major kernel
   ClsTables cls;             // class-major two-phase kernel (uniform models, long rows)
   bool cls_default = false;  // variant 0 picks it
   int cls_stagger = 0;       // see ClsParams::stagger_cycles (env CMPY_CLS_STAGGER overrides)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
 
   ~HubbardOp() override {
-    up.release(); dn.release(); seg.release(); cls.release();
+    up.release(); dn.release(); seg.release(); cls.release(); lng.release();
     cudaFree(d_hop); cudaFree(d_u);
   }
 
@@ -110,6 +111,11 @@ struct HubbardOp : cmpy_op_s {
     if (use_variant >= 5 && use_variant <= 7 && !(cls.ok && UNI))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant not available for this sector");
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
+    if (use_variant == 8 && !(lng.ok && UNI && aligned16 && !p.with_up && !LZ && (p.num_dn % 2 == 0)))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant not available for this call");
+    if (use_variant == 8 || (use_variant == 0 && lng.ok && UNI && aligned16 && !p.with_up && !LZ &&
+                             (p.num_dn % 2 == 0)))
+      return launch_long(p, st);
     if (use_variant >= 5 && use_variant <= 7 && !aligned16)
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant needs 16-byte aligned vectors");
     // default: the segment kernel for the full H.v (its up-hop gathers overlap the shared-memory
@@ -195,6 +201,38 @@ struct HubbardOp : cmpy_op_s {
     else if (cls_shape == 2) hub_cls_kernel<LZ, 768, 12><<<(int)g, 768, cls.smem, st>>>(cp);
     else hub_cls_kernel<LZ, 1024, 8><<<(int)g, 1024, cls.smem, st>>>(cp);
     KERNEL_CHECK();
+    return CMPY_OK;
+  }
+
+  // dn-only pass over rows longer than shared memory: one launch per popcount of the top bits
+  int launch_long(HubParams& p, cudaStream_t st) {
+    for (auto& S : lng.sets) {
+      ClsParams cp;
+      cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.cls.d_pair_seg;
+      cp.e_dn_const = lng.e_dn_const; cp.stagger_cycles = 0;
+      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb;
+      cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
+      cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
+      i64 g = sm_count;
+      const i64 items = p.nrows * S.ntop;
+      if (g > items) g = items;
+      hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      KERNEL_CHECK();
+    }
+    return CMPY_OK;
+  }
+
+  int configure_long(int n_dn, const int* s1, const int* s2, const double* eps) {
+    if (!(uniform && eps_uniform) || num_sites <= LONG_RBITS) return CMPY_OK;
+    int rc = build_long_tables(lng, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin);
+    if (rc || !lng.ok) return rc;
+    rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, true>, smem_optin);
+    if (rc) return rc;
+    for (auto& S : lng.sets) {
+      int nb = 0;
+      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<false, 1024, 8, true>, 1024, S.cls.smem));
+      if (nb < 1) { lng.release(); return CMPY_OK; }
+    }
     return CMPY_OK;
   }
 

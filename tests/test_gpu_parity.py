@@ -804,3 +804,64 @@ def test_matvec_batch_pipelined_host_vectors(cm):
     assert relerr(res[-2].numpy(), h.matvec(xs[-2].numpy())) < HV_RTOL
     with pytest.raises(TypeError):
         h.matvec_batch([torch.zeros(3, dtype=torch.float64)])
+
+
+# ---------------------------------------------------------------------------------------
+# K4 long rows (more than 16 sites): sub-row launches of the class-major kernel
+# ---------------------------------------------------------------------------------------
+
+def _lattice_3x6():
+    nb = []
+    for r in range(3):
+        for c in range(6):
+            i = 6 * r + c
+            if c + 1 < 6:
+                nb.append([i, i + 1])
+            if r + 1 < 3:
+                nb.append([i, i + 6])
+    return nb
+
+
+@pytest.mark.parametrize("L,nu,nd,nbfn,kw", [
+    (17, 2, 8, lambda: chain(17), dict(inter=4.0, mu=2.0, hop=1.0)),
+    (17, 1, 5, lambda: chain(17, True), dict(inter=3.0, eps=0.2, mu=0.5, hop=-0.7)),
+    (18, 1, 9, _lattice_3x6, dict(inter=4.0, mu=2.0, hop=1.0)),
+    (20, 1, 10, lambda: chain(20), dict(inter=4.0, mu=2.0, hop=1.0)),
+    (19, 1, 9, lambda: chain(19) + [[3, 17], [12, 18], [16, 18]], dict(inter=2.0, mu=1.0, hop=0.5)),
+])
+def test_hv_long_rows(cm, L, nu, nd, nbfn, kw):
+    """dn strings of more than 16 sites: the long-row variant (8) against the global-gather kernel
+    (1) on the row-slab entry point, and the full H.v assembled from two long-row passes (the
+    sharded operator with one rank, all-to-all choreography) against the oracle."""
+    import torch
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.dist import ShardedHubbardOperator
+
+    nb = nbfn()
+    model = HubbardModel(L, nb, **kw)
+    h = model.hamilton_operator(nu, nd)
+    n = h.shape[0]
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n)
+    xt = torch.from_numpy(x).cuda()
+    num_up = len(h.up_states)
+    h.set_variant(1)
+    ref_dn = h.apply_rows(xt, 0, num_up).cpu().numpy()
+    h.set_variant(8)
+    got = h.apply_rows(xt, 0, num_up).cpu().numpy()
+    assert relerr(got, ref_dn) < HV_RTOL
+    acc = torch.ones(n, dtype=torch.float64, device="cuda")
+    h.apply_rows(xt, 0, num_up, out=acc, accumulate=True)
+    assert relerr(acc.cpu().numpy() - 1.0, ref_dn) < 1e-11
+    # a slab that does not start at row 0
+    if num_up > 1:
+        nd_ = len(h.dn_states)
+        part = h.apply_rows(xt[nd_:], 1, num_up - 1).cpu().numpy()
+        assert relerr(part, ref_dn[nd_:]) < HV_RTOL
+    h.set_variant(0)
+    up, dn = orc.enumerate_states(L, nu), orc.enumerate_states(L, nd)
+    ref = orc.hubbard_matvec_free(up, dn, nb, kw.get("inter", 0.0), kw.get("eps", 0.0) - kw.get("mu", 0.0),
+                                  kw.get("hop", 1.0), x, width=L)
+    sh = ShardedHubbardOperator(model, nu, nd, exchange="a2a")
+    y = sh.apply_local(xt).cpu().numpy()
+    assert relerr(y, ref) < HV_RTOL
