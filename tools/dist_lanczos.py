@@ -39,6 +39,13 @@ for _ in range(reps):
 e1_.record(); dist.barrier(); torch.cuda.synchronize()
 ms = torch.tensor([e0_.elapsed_time(e1_) / reps], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 hv_ms = float(ms)
+phases = None
+if op.exchange == "peer":
+    ph = op.profile_phases(x, y, reps=3)
+    t = torch.tensor([ph[k] for k in ("dn_pass", "push", "up_pass", "pull", "barrier")], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    phases = dict(zip(("dn_pass", "push", "up_pass", "pull", "barrier"), [float(v) for v in t]))
+    phases["nvlink_bytes_per_transpose"] = ph["nvlink_bytes_per_transpose"]
 del x, y
 torch.cuda.empty_cache()
 def cb(nit, e):
@@ -55,7 +62,7 @@ if rank == 0:
                hv_ms=hv_ms, hv_algorithmic_gbs_per_gpu=16.0 * dim / world / (hv_ms * 1e-3) / 1e9,
                nvlink_out_gbs_per_gpu=p.bytes_out_per_hv() / (hv_ms * 1e-3) / 1e9,
                lanczos_s=t_lz, iterations=nit, converged=bool(conv), e0=e0,
-               ms_per_iteration=1e3 * t_lz / max(nit, 1), max_mem_gb=mem)
+               ms_per_iteration=1e3 * t_lz / max(nit, 1), max_mem_gb=mem, phases_ms=phases)
     if U == 0.0:  # free fermions: E0 = 2 * sum of the n lowest levels of the hopping matrix (mu = 0)
         h = np.zeros((L, L))
         for i, j in nb:
