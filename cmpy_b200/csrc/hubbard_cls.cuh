@@ -276,13 +276,16 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
     const uint32_t dtop = LONG ? cp.lg.top_val[ti] : 0u;
     __syncthreads();  // previous row fully consumed (first pass: tables loaded, xs zeroed)
     CLS_TICK(0)
-    // ---- stage the row: natural order -> class-major padded layout ----
-    for (int it = warp; it < L.nb; it += NW) {
-      const int dh = item_b[it];
-      const int sk = L.S[hi_k[dh]];
-      const double* __restrict__ src = xr + hi_goff[dh];
-      double* __restrict__ dst = xs + hi_sbase[dh];
-      for (int r = lane; r < sk; r += 32) dst[r] = __ldg(src + r);
+    // ---- stage the row: natural order -> class-major padded layout (16-byte loads, the same
+    //      column-pair -> slot map as phase C) ----
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int pi = tid + i * NT;
+      if (2 * pi < ndi) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(xr) + pi);
+        xs[slots[i] & 0xffffu] = v.x;
+        xs[slots[i] >> 16] = v.y;
+      }
     }
     const int tb0 = LONG ? cp.lg.tb_ptr[ti] : 0;
     const int cu = LONG ? cp.lg.tb_ptr[ti + 1] - tb0 : ((WITH_UP && p.with_up) ? (int)p.cnt_up[u] : 0);
