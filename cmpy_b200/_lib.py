@@ -65,6 +65,7 @@ SIGNATURES = {
     "cmpy_pole_sum": (c_int, [_p, _p, c_int64, _p, c_int64, _p, c_int, _p]),
     "cmpy_transpose": (c_int, [_p, c_int64, c_int64, c_int64, _p, c_int64, c_int, _p]),
     "cmpy_copy2d": (c_int, [_p, c_int64, c_int64, c_int64, _p, c_int64, c_int, _p]),
+    "cmpy_hubbard_set_grid_limit": (c_int, [_p, c_int]),
     "cmpy_transpose_push": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                     POINTER(_p), _p]),
     "cmpy_transpose_pull_acc": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),

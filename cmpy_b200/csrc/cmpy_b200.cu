@@ -263,6 +263,14 @@ API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
   return CMPY_OK;
 }
 
+API int cmpy_hubbard_set_grid_limit(cmpy_op_t op, int max_ctas) {
+  ARG_CHECK(op && max_ctas >= 0, "bad argument");
+  HubbardOp* h = dynamic_cast<HubbardOp*>(op);
+  ARG_CHECK(h, "set_grid_limit: not a Hubbard operator");
+  h->grid_limit = max_ctas;
+  return CMPY_OK;
+}
+
 API int cmpy_op_diagonal(cmpy_op_t op, double* d_diag, void* stream) {
   ARG_CHECK(op && d_diag, "null argument");
   return op->diagonal(d_diag, as_stream(stream));

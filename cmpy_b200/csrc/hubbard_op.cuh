@@ -43,6 +43,7 @@ struct HubbardOp : cmpy_op_s {
   LongTables lng;            // rows of more than 16 sites: sub-row launches of the class-major kernel
   ClsTables cls;             // class-major two-phase kernel (uniform models, long rows)
   bool cls_default = false;  // variant 0 picks it
+  int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_stagger = 0;       // see ClsParams::stagger_cycles (env CMPY_CLS_STAGGER overrides)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
 
@@ -195,6 +196,7 @@ struct HubbardOp : cmpy_op_s {
     cp.hp = p; cp.lay = cls.lay; cp.blob = cls.d_blob; cp.pair_seg = cls.d_pair_seg; cp.e_dn_const = cls.e_dn_const;
     cp.stagger_cycles = p.with_up ? cls_stagger : 0;
     i64 g = sm_count;
+    if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
     if (!p.with_up) hub_cls_kernel<LZ, 1024, 0><<<(int)g, 1024, cls.smem, st>>>(cp);
     else if (cls_shape == 1) hub_cls_kernel<LZ, 512, 16><<<(int)g, 512, cls.smem, st>>>(cp);
@@ -214,6 +216,7 @@ struct HubbardOp : cmpy_op_s {
       cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
       cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
       i64 g = sm_count;
+      if (grid_limit > 0 && g > grid_limit) g = grid_limit;
       const i64 items = p.nrows * S.ntop;
       if (g > items) g = items;
       hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);

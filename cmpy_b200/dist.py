@@ -183,6 +183,11 @@ class ShardedHubbardOperator:
         self._peer_yt = (ctypes.c_void_p * self.world)(*[int(a) for a in self._h_yt.buffer_ptrs])
         self._cb = (ctypes.c_int64 * (self.world + 1))(*p.col_bounds)
         self._side = torch.cuda.Stream()
+        # SMs left to the push transpose while the local dn pass runs (the class-major kernel takes
+        # one CTA and all shared memory per SM, so without this the two kernels serialise)
+        import os
+        self._sm_count = torch.cuda.get_device_properties(_lib.device()).multi_processor_count
+        self._push_sms = int(os.environ.get("CMPY_PUSH_SMS", "32"))
 
     def _apply_local_peer(self, x_local, out, accumulate=False):
         torch = _lib.require_cuda()
@@ -199,10 +204,13 @@ class ShardedHubbardOperator:
         with torch.cuda.stream(self._side):
             _lib.check(L.cmpy_transpose_push(_lib.ptr(x_local), nrows, nd, r0, nu, self.world, self._cb,
                                              self._peer_xt, _lib.stream_ptr()), "cmpy_transpose_push")
+        limit = self._sm_count - self._push_sms if (self.world > 1 and 0 < self._push_sms < self._sm_count) else 0
+        _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, limit), "cmpy_hubbard_set_grid_limit")
         if accumulate:
             be.apply_rows(x_local, r0, nrows, out, accumulate=True)
         else:
             be.apply_rows(x_local, r0, nrows, out)
+        _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, 0), "cmpy_hubbard_set_grid_limit")
         main.wait_stream(self._side)
         self._h_xt.barrier(channel=0)          # all pushes have landed
         be.apply_rows_t(self._xt, c0, ncols, self._yt)   # up hops, row-local in the dn-major slab

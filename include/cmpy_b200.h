@@ -187,6 +187,11 @@ int cmpy_transpose(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_
 int cmpy_copy2d(const double* d_in, int64_t nrows, int64_t ncols, int64_t ld_in,
                 double* d_out, int64_t ld_out, int accumulate, void* stream);
 
+/* Caps the number of CTAs of the persistent one-CTA-per-SM row kernels behind
+ * cmpy_hubbard_apply_rows (0 = no cap).  The sharded operator leaves a few SMs to the peer
+ * transpose that runs concurrently with the local dn pass (cmpy_b200/dist.py). */
+int cmpy_hubbard_set_grid_limit(cmpy_op_t op, int max_ctas);
+
 /* ---- K9 over NVLink peer memory (one process per GPU, slabs in symmetric memory) ----
  * push: for the local slab of up-rows [row0, row0+nrows) (row-major nrows x num_dn) and every
  *       rank q owning the dn-columns [col_bounds[q], col_bounds[q+1]):
