@@ -5,6 +5,7 @@
 #include "sector.cuh"
 #include "hubbard.cuh"
 #include "hubbard_seg.cuh"
+#include "hubbard_cls.cuh"
 #include "hubbard_op.cuh"
 #include "lanczos.cuh"
 #include "greens.cuh"

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "sector.cuh"
 #include "hubbard.cuh"
+#include "hubbard_cls.cuh"
 
 #define HEIS_MAX_BONDS 64
 
@@ -28,6 +29,7 @@ struct HeisBonds {
 };
 
 struct HeisParams {
+  int pt_filter;            // >= 0: only rows whose hi part has this popcount (rest: class-major path)
   int lo_bits, n_up, all_states;
   i64 nhi;
   const i64* off;           // [nhi + 1]
@@ -67,7 +69,7 @@ __global__ void heis_row_kernel(HeisParams p) {
     const uint32_t hi = (uint32_t)hi64;
     const i64 base = p.off[hi64];
     const i64 len = p.off[hi64 + 1] - base;
-    if (len == 0) continue;
+    if (len == 0 || (p.pt_filter >= 0 && __popc(hi) != p.pt_filter)) continue;
     const i64 cbase = p.cls_off[heis_cls(p, hi)];
     const double* __restrict__ xr = p.x + base;
     for (i64 r = tid; r < len; r += nt) xs[r] = xr[r];
@@ -159,13 +161,24 @@ struct HeisenbergOp : cmpy_op_s {
   i64* d_off = nullptr; uint32_t* d_lo_list = nullptr; i64* d_cls_off = nullptr;
   uint16_t* d_lo_rank = nullptr; HeisBonds* d_bonds = nullptr;
   int threads = 256, blocks_per_sm = 1;
+  // fast path for more than 16 sites: sub-row launches of the class-major kernel (hubbard_cls.cuh)
+  LongTables lng;
+  std::vector<int> slow_pt;   // popcounts of the high part left to heis_row_kernel
+  SpinDiag sd;
+  double w_hop = 0.0;
+  uint32_t* d_zero_u32 = nullptr;
+  double* d_zero_f64 = nullptr;
+  bool fast_ok = false;
 
   ~HeisenbergOp() override {
     cudaFree(d_off); cudaFree(d_lo_list); cudaFree(d_cls_off); cudaFree(d_lo_rank); cudaFree(d_bonds);
+    cudaFree(d_zero_u32); cudaFree(d_zero_f64);
+    lng.release();
   }
 
   HeisParams params() const {
     HeisParams p;
+    p.pt_filter = -1;
     p.lo_bits = lo_bits; p.n_up = n_up; p.all_states = all_states; p.nhi = nhi;
     p.off = d_off; p.lo_list = d_lo_list; p.cls_off = d_cls_off; p.lo_rank = d_lo_rank;
     p.bonds = d_bonds; p.x = nullptr; p.y = nullptr;
@@ -179,6 +192,7 @@ struct HeisenbergOp : cmpy_op_s {
     ARG_CHECK(N >= 1 && N <= 32, "heisenberg: 1 <= num_sites <= 32");
     ARG_CHECK(all_states || nup <= N, "heisenberg: n_up out of range");
     lo_bits = N / 2; if (lo_bits < 1) lo_bits = 1; if (lo_bits > 16) lo_bits = 16;
+    if (N > LONG_RBITS && !all_states) lo_bits = LONG_RBITS;  // same split as the class-major fast path
     if (lo_bits > N) lo_bits = N;
     hi_bits = N - lo_bits;
     ARG_CHECK(hi_bits <= 16, "heisenberg: internal split");
@@ -254,6 +268,8 @@ struct HeisenbergOp : cmpy_op_s {
     CU_CHECK(cudaMemcpy(d_cls_off, cls_off.data(), sizeof(i64) * (lo_bits + 2), cudaMemcpyHostToDevice));
     CU_CHECK(cudaMalloc(&d_bonds, sizeof(HeisBonds)));
     CU_CHECK(cudaMemcpy(d_bonds, &hb, sizeof(HeisBonds), cudaMemcpyHostToDevice));
+    int rcf = configure_fast(bi, bj, mult, jj, jz);
+    if (rcf) return rcf;
     // launch config
     size_t smem = sizeof(double) * (size_t)max_len;
     i64 t = ((max_len + 3) / 4 + 31) / 32 * 32;
@@ -269,7 +285,95 @@ struct HeisenbergOp : cmpy_op_s {
     return CMPY_OK;
   }
 
+  // Class-major fast path: uniform bond weights, fixed magnetisation, more than 16 sites.
+  int configure_fast(const std::vector<int>& bi, const std::vector<int>& bj, const std::vector<int>& mult,
+                     double jj, double jz) {
+    fast_ok = false;
+    if (all_states || num_sites <= LONG_RBITS || bi.empty()) return CMPY_OK;
+    for (size_t k = 1; k < mult.size(); ++k) if (mult[k] != mult[0]) return CMPY_OK;
+    w_hop = mult[0] * (0.25 * jj / 2);
+    const double dz = mult[0] * (0.25 * jz);
+    memset(&sd, 0, sizeof(sd));
+    for (size_t k = 0; k < bi.size(); ++k) {
+      const int delta = bj[k] - bi[k];
+      int i = 0;
+      for (; i < sd.ndelta; ++i) if (sd.delta[i] == delta) break;
+      if (i == sd.ndelta) {
+        if (sd.ndelta == 4) return CMPY_OK;
+        sd.delta[sd.ndelta++] = delta;
+      }
+      sd.dmask[i] |= 1u << bi[k];
+    }
+    sd.e0 = dz * (double)bi.size();
+    sd.escale = -2.0 * dz;
+    const double eps0[1] = {0.0};
+    slow_pt.clear();
+    int rc = build_long_tables(lng, num_sites, n_up, size, (int)bi.size(), bi.data(), bj.data(), 0, eps0,
+                               smem_optin, &slow_pt);
+    if (rc) return rc;
+    if (!lng.ok) return CMPY_OK;
+    CU_CHECK(cudaMalloc(&d_zero_u32, 16)); CU_CHECK(cudaMemset(d_zero_u32, 0, 16));
+    CU_CHECK(cudaMalloc(&d_zero_f64, 16)); CU_CHECK(cudaMemset(d_zero_f64, 0, 16));
+    rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, true, true>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, true, true>, smem_optin);
+    if (rc) return rc;
+    fast_ok = true;
+    return CMPY_OK;
+  }
+
+  int apply_fast(const double* x, double* y, const LzCtx& lz, cudaStream_t st) {
+    HubParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.num_up = 1; hp.num_dn = size; hp.up_states = d_zero_u32; hp.e_up = d_zero_f64;
+    hp.num_sites = num_sites; hp.u0 = 0.0; hp.hop0 = w_hop;
+    hp.row0 = 0; hp.nrows = 1; hp.with_up = 0; hp.accumulate = 0;
+    hp.x = x; hp.y = y;
+    hp.lz.enabled = 0; hp.lz.partials = d_partials; hp.lz.ticket = d_ticket;
+    int launches = 0;
+    for (auto& S : lng.sets) {
+      ClsParams cp;
+      cp.hp = hp; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
+      cp.e_dn_const = 0.0; cp.stagger_cycles = 0; cp.sd = sd;
+      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb; cp.lg.shift = S.shift;
+      cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
+      cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
+      i64 g = sm_count;
+      if (g > S.ntop) g = S.ntop;
+      if (lz.enabled) {
+        cp.hp.lz = lz; cp.hp.lz.partials = d_partials; cp.hp.lz.ticket = d_ticket;
+        cp.hp.lz.enabled = launches == 0 ? 1 : 2;
+        hub_cls_kernel<true, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      } else {
+        hub_cls_kernel<false, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      }
+      KERNEL_CHECK();
+      ++launches;
+    }
+    // the classes the class-major kernel cannot take (sub-rows of odd length): generic row kernel
+    for (int pt : slow_pt) {
+      HeisParams p = params();
+      p.x = x; p.y = y; p.pt_filter = pt;
+      size_t smem = sizeof(double) * (size_t)max_len;
+      i64 g = (i64)sm_count * blocks_per_sm;
+      if (g > nhi) g = nhi;
+      if (lz.enabled) {
+        p.lz = lz; p.lz.partials = d_partials; p.lz.ticket = d_ticket;
+        p.lz.enabled = launches == 0 ? 1 : 2;
+        heis_row_kernel<true><<<(int)g, threads, smem, st>>>(p);
+      } else {
+        heis_row_kernel<false><<<(int)g, threads, smem, st>>>(p);
+      }
+      KERNEL_CHECK();
+      ++launches;
+    }
+    return CMPY_OK;
+  }
+
   int apply(const double* x, double* y, const LzCtx& lz, cudaStream_t st) override {
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (variant == 5 && !(fast_ok && aligned16))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant not available for this spin sector");
+    if (fast_ok && aligned16 && variant != 1) return apply_fast(x, y, lz, st);
     HeisParams p = params();
     p.x = x; p.y = y;
     size_t smem = sizeof(double) * (size_t)max_len;

@@ -83,7 +83,8 @@ __device__ __forceinline__ void lz_finish(const LzCtx& lz, int j, double dot, do
   if (LZ) {
     double bsum = block_sum(dot, red);
     double total;
-    if (grid_sum_last(bsum, lz.partials, lz.ticket, red, &total)) lz.alpha[j] = total;
+    // enabled == 2: a later launch of the same H.v (the operator is split over several kernels)
+    if (grid_sum_last(bsum, lz.partials, lz.ticket, red, &total)) lz.alpha[j] = (lz.enabled == 2 ? lz.alpha[j] : 0.0) + total;
   }
 }
 

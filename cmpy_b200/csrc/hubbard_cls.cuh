@@ -67,6 +67,8 @@ struct LongCtx {
   int ntop;                 // sub-rows per up-row in this launch
   int row_len;              // amplitudes per sub-row
   int nsb;                  // bonds straddling site 15|16
+  int shift;                // 1: every sub-row of this launch starts at an ODD element of the vector;
+                            // the 16-byte column pairs are then (2i-1, 2i) instead of (2i, 2i+1)
   const uint32_t* top_val;  // [ntop]     dtop
   const int* sub_off;       // [ntop]     offset of the sub-row inside the dn row
   const int* tb_ptr;        // [ntop + 1] top-bond hop lists
@@ -76,12 +78,25 @@ struct LongCtx {
   const uint32_t* sb_map;   // [nsb][2][row_len] rank in the source sub-row | parity << 30 | valid << 31
 };
 
+// Heisenberg / XXZ flavour of the same machinery (an up spin is a hard-core boson: hops without
+// sign, uniform amplitude): only the diagonal differs,
+//   E(s) = dz * (n_bonds - 2 * #antiparallel bonds),  #antiparallel = sum_i popc((s ^ (s >> delta_i)) & mask_i)
+// with the bonds grouped by their site distance delta_i (ref: cmpy/models/heisenberg.py:19-40).
+struct SpinDiag {
+  int ndelta;
+  int delta[4];
+  uint32_t dmask[4];
+  double e0, escale;   // E = e0 + escale * #antiparallel
+};
+
 struct ClsParams {
   HubParams hp;
   ClsLayout lay;
   LongCtx lg;
+  SpinDiag sd;
   const unsigned char* blob;
-  const uint16_t* pair_seg;  // global: natural segment ordinal of column 2*i | straddle << 15
+  const uint16_t* pair_seg;  // global: natural segment ordinal of the first valid column of pair i |
+                             // (second column starts the next segment) << 15; one table per shift
   double e_dn_const;
   int stagger_cycles;        // start delay of CTA b: (b % 3) * stagger_cycles (de-phases the SMs)
 };
@@ -93,8 +108,9 @@ struct __align__(16) UpEnt2 { int off; int pad; double coef; };  // element offs
 // the '-' part does n += x[e0]; p -= x[e1]; odd-length parts are padded with a slot holding 0.
 
 // ---- phase A body: one (k, r) pair, T blocks of 32 dh-segments (lanes along jj) ----
-template <int T>
-__device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const double* __restrict__ xs,
+template <int T, bool SPIN>
+__device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const SpinDiag& sd,
+                                            const double* __restrict__ xs,
                                             double* __restrict__ ys, const uint8_t* __restrict__ ll_ent,
                                             const uint16_t* __restrict__ dh_list, uint32_t pp, int k,
                                             int r, uint32_t dlbits, uint32_t ups, double eu, double u0,
@@ -130,7 +146,15 @@ __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const double* __
   for (int t = 0; t < T; ++t) {
     if (lane + 32 * t < hk) {
       const uint32_t dns = ((uint32_t)dhl[32 * t] << L.m) | dlbits;
-      const double diag = eu + u0 * (double)__popc(ups & dns);
+      double diag;
+      if (SPIN) {  // ups carries the top bits of the spin string (dtop << 16)
+        const uint32_t sfull = ups | dns;
+        int cnt = 0;
+        for (int i = 0; i < sd.ndelta; ++i) cnt += __popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
+        diag = sd.e0 + sd.escale * (double)cnt;
+      } else {
+        diag = eu + u0 * (double)__popc(ups & dns);
+      }
       ys[o[t] + r] = diag * xs[o[t] + r] + hop0 * (ap[t] - an[t]);
     }
   }
@@ -196,7 +220,7 @@ __device__ __forceinline__ int seg_delta_g(const ClsParams& cp, int si) {
 
 // smem: [table blob][xs: xs_elems + CLS_ZREG doubles][ys: xs_elems doubles]
 // UPG = 0 compiles the up-hop gathers out (row-slab launches of the sharded operator).
-template <bool LZ, int NT, int UPG_, bool LONG = false>
+template <bool LZ, int NT, int UPG_, bool LONG = false, bool SPIN = false>
 __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   constexpr bool WITH_UP = UPG_ > 0;
   constexpr int UPG = WITH_UP ? UPG_ : 1;
@@ -241,17 +265,21 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   const double u0 = p.u0, hop0 = p.hop0;
 
   // Row-invariant phase-C bookkeeping: ys slots of the column pairs this thread owns.
-  constexpr int MAXP = (16384 / 2 + NT - 1) / NT;
+  constexpr int MAXP = (13312 / 2 + NT - 1) / NT;   // rows are limited by shared memory (< 13.2 K)
+  const int shift = LONG ? cp.lg.shift : 0;
+  const int npairs = (ndi + shift + 1) / 2;
   uint32_t slots[MAXP];
 #pragma unroll
   for (int i = 0; i < MAXP; ++i) {
     const int pi = tid + i * NT;
     slots[i] = 0;
-    if (2 * pi < ndi) {
+    if (pi < npairs) {
       const uint32_t ps = cp.pair_seg[pi];
-      const int si = (int)(ps & 0x7fffu), d = 2 * pi;
-      const int slot0 = d + seg_delta_g(cp, si);
-      const int slot1 = (ps >> 15) ? d + 1 + seg_delta_g(cp, si + 1) : slot0 + 1;
+      const int si = (int)(ps & 0x7fffu), d = 2 * pi - shift;
+      int slot0 = d + seg_delta_g(cp, si);
+      int slot1 = d + 1 + seg_delta_g(cp, si + (int)(ps >> 15));
+      if (d < 0) slot0 = slot1;          // column -1 / ndi belong to the neighbouring sub-rows
+      if (d + 1 >= ndi) slot1 = slot0;
       slots[i] = (uint32_t)slot0 | ((uint32_t)slot1 << 16);
     }
   }
@@ -281,10 +309,18 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
 #pragma unroll
     for (int i = 0; i < MAXP; ++i) {
       const int pi = tid + i * NT;
-      if (2 * pi < ndi) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(xr) + pi);
-        xs[slots[i] & 0xffffu] = v.x;
-        xs[slots[i] >> 16] = v.y;
+      if (pi < npairs) {
+        const int d = 2 * pi - shift;
+        const bool v0 = d >= 0, v1 = d + 1 < ndi;
+        if (v0 && v1) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(xr + d));
+          xs[slots[i] & 0xffffu] = v.x;
+          xs[slots[i] >> 16] = v.y;
+        } else if (v0) {
+          xs[slots[i] & 0xffffu] = __ldg(xr + d);
+        } else if (v1) {
+          xs[slots[i] >> 16] = __ldg(xr + d + 1);
+        }
       }
     }
     const int tb0 = LONG ? cp.lg.tb_ptr[ti] : 0;
@@ -305,8 +341,8 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
       }
       s_up[tid] = ue;
     }
-    const uint32_t ups = p.up_states[u];
-    const double eu = p.e_up[u] + ediag0 + (LONG ? u0 * (double)__popc((ups >> 16) & dtop) : 0.0);
+    const uint32_t ups = SPIN ? (dtop << 16) : p.up_states[u];
+    const double eu = SPIN ? 0.0 : p.e_up[u] + ediag0 + (LONG ? u0 * (double)__popc((ups >> 16) & dtop) : 0.0);
     CLS_TICK(1)
     __syncthreads();
     CLS_TICK(2)
@@ -323,9 +359,9 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
       const uint32_t pp = ll_ptr[q];
       const uint32_t dlbits = dl_of_q[q];
       const int hk = L.H[k], r = q - L.qoff[k];
-      if (hk <= 32) cls_phase_a<1>(L, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
-      else if (hk <= 64) cls_phase_a<2>(L, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
-      else cls_phase_a<3>(L, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+      if (hk <= 32) cls_phase_a<1, SPIN>(L, cp.sd, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+      else if (hk <= 64) cls_phase_a<2, SPIN>(L, cp.sd, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+      else cls_phase_a<3, SPIN>(L, cp.sd, xs, ys, ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
     }
     CLS_TICK(3)
     __syncthreads();
@@ -347,17 +383,22 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
 #pragma unroll
     for (int i = 0; i < MAXP; ++i) {
       const int pi = tid + i * NT;
-      if (2 * pi >= ndi) break;
-      const int d = 2 * pi;
+      if (pi >= npairs) break;
+      const int d = 2 * pi - shift;
+      const bool v0 = d >= 0, v1 = d + 1 < ndi, full = v0 && v1;
       const double* __restrict__ xg = xr + d;
       const int slot0 = (int)(slots[i] & 0xffffu), slot1 = (int)(slots[i] >> 16);
       double a0, a1;
+      auto load2 = [&](int off) -> double2 {   // 16-byte load; edge pairs (one valid column) scalar
+        if (full) return __ldg(reinterpret_cast<const double2*>(xg + off));
+        return make_double2(v0 ? __ldg(xg + off) : 0.0, v1 ? __ldg(xg + off + 1) : 0.0);
+      };
       if (WITH_UP) {
         double2 gth[UPG];
 #pragma unroll
         for (int q = 0; q < UPG; ++q) {
           const int off = s_up[q].off;
-          gth[q] = (q < cu) ? __ldg(reinterpret_cast<const double2*>(xg + off)) : make_double2(0.0, 0.0);
+          gth[q] = (q < cu) ? load2(off) : make_double2(0.0, 0.0);
         }
         a0 = ys[slot0]; a1 = ys[slot1];
 #pragma unroll
@@ -370,7 +411,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
 #pragma unroll
           for (int q = 0; q < UPG; ++q) {
             const int off = s_up[q0 + q].off;
-            gth[q] = (q0 + q < cu) ? __ldg(reinterpret_cast<const double2*>(xg + off)) : make_double2(0.0, 0.0);
+            gth[q] = (q0 + q < cu) ? load2(off) : make_double2(0.0, 0.0);
           }
 #pragma unroll
           for (int q = 0; q < UPG; ++q) {
@@ -387,27 +428,31 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
           const int2 src = cp.lg.sb_src[sb * cp.lg.ntop + ti];
           if (src.y & 1) {
             const uint32_t* map = cp.lg.sb_map + ((size_t)(2 * sb + ((src.y >> 1) & 1)) * ndi + d);
-            const uint2 e = *reinterpret_cast<const uint2*>(map);
+            const uint32_t e0 = v0 ? map[0] : 0u, e1 = v1 ? map[1] : 0u;
             const uint32_t ptop = (uint32_t)(src.y >> 2) & 1u;
             const double* __restrict__ xsrc = xr + src.x;
-            if (e.x >> 31) a0 += flip_sign(hop0 * __ldg(xsrc + (e.x & 0x3fffffffu)), ((e.x >> 30) & 1u) ^ ptop);
-            if (e.y >> 31) a1 += flip_sign(hop0 * __ldg(xsrc + (e.y & 0x3fffffffu)), ((e.y >> 30) & 1u) ^ ptop);
+            if (e0 >> 31) a0 += flip_sign(hop0 * __ldg(xsrc + (e0 & 0x3fffffffu)), ((e0 >> 30) & 1u) ^ ptop);
+            if (e1 >> 31) a1 += flip_sign(hop0 * __ldg(xsrc + (e1 & 0x3fffffffu)), ((e1 >> 30) & 1u) ^ ptop);
           }
         }
       }
-      double2* yp = reinterpret_cast<double2*>(yr + d);
+      double w0 = a0, w1 = a1;
       if (LZ) {
         const double x0 = xs[slot0], x1 = xs[slot1];
-        double w0 = s1 * a0, w1 = s1 * a1;
-        if (has_prev) { const double2 yo = *yp; w0 -= s2 * yo.x; w1 -= s2 * yo.y; }
-        *yp = make_double2(w0, w1);
-        dot += (s1 * x0) * w0 + (s1 * x1) * w1;
+        w0 = s1 * a0; w1 = s1 * a1;
+        if (has_prev) {
+          if (v0) w0 -= s2 * yr[d];
+          if (v1) w1 -= s2 * yr[d + 1];
+        }
+        if (v0) dot += (s1 * x0) * w0;
+        if (v1) dot += (s1 * x1) * w1;
       } else if (p.accumulate) {
-        const double2 yo = *yp;
-        *yp = make_double2(yo.x + a0, yo.y + a1);
-      } else {
-        *yp = make_double2(a0, a1);
+        if (v0) w0 += yr[d];
+        if (v1) w1 += yr[d + 1];
       }
+      if (full) *reinterpret_cast<double2*>(yr + d) = make_double2(w0, w1);
+      else if (v0) yr[d] = w0;
+      else if (v1) yr[d + 1] = w1;
     }
     CLS_TICK(5)
   }
@@ -425,11 +470,15 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
 struct ClsTables {
   ClsLayout lay;
   unsigned char* d_blob = nullptr;
-  uint16_t* d_pair_seg = nullptr;
+  uint16_t* d_pair_seg = nullptr;    // pairs (2i, 2i+1)
+  uint16_t* d_pair_seg1 = nullptr;   // pairs (2i-1, 2i): sub-rows that start at an odd element
   bool ok = false;
   double e_dn_const = 0.0;
   size_t smem = 0;
-  void release() { cudaFree(d_blob); cudaFree(d_pair_seg); d_blob = nullptr; d_pair_seg = nullptr; ok = false; }
+  void release() {
+    cudaFree(d_blob); cudaFree(d_pair_seg); cudaFree(d_pair_seg1);
+    d_blob = nullptr; d_pair_seg = nullptr; d_pair_seg1 = nullptr; ok = false;
+  }
 };
 
 // Builds the class-major tables for the dn species.  ok=false (no error) when the sector is
@@ -481,7 +530,8 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   }
   std::vector<int> hi_k(nhi, 0xff), hi_goff(nhi, 0), hi_sbase(nhi, 0), dh_list(std::max(nseg, 1), 0);
   std::vector<int> seg_delta;  // natural order
-  std::vector<uint16_t> pair_seg((size_t)num_dn / 2, 0);
+  std::vector<uint16_t> pair_seg((size_t)num_dn / 2, 0), pair_seg1((size_t)num_dn / 2 + 1, 0);
+  std::vector<int> seg_of((size_t)num_dn, 0);
   {
     std::vector<int> fill(m + 1, 0);
     i64 off = 0;
@@ -494,14 +544,23 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
       dh_list[L.hoff[k] + fill[k]] = dh;
       ++fill[k];
       seg_delta.push_back(hi_sbase[dh] - hi_goff[dh]);
-      for (i64 d = off; d < off + L.S[k]; ++d)
+      for (i64 d = off; d < off + L.S[k]; ++d) {
+        seg_of[d] = ordinal;
         if ((d & 1) == 0) pair_seg[d / 2] = (uint16_t)(ordinal | ((d + 1 == off + L.S[k]) ? 0x8000 : 0));
+      }
       off += L.S[k];
       ++ordinal;
     }
     if (off != num_dn) return cmpy_fail(CMPY_ERR_ARG, "class tables: size mismatch");
     seg_delta.push_back(0);
     if (ordinal >= 0x8000) return CMPY_OK;
+    // shifted pairs (2i-1, 2i): ordinal of the first valid column, flag = second column in the next segment
+    for (i64 pi = 0; pi <= num_dn / 2; ++pi) {
+      const i64 d0 = 2 * pi - 1, d1 = 2 * pi;
+      if (d0 < 0) pair_seg1[pi] = (uint16_t)seg_of[d1];
+      else if (d1 >= num_dn) pair_seg1[pi] = (uint16_t)seg_of[d0];
+      else pair_seg1[pi] = (uint16_t)(seg_of[d0] | (seg_of[d1] != seg_of[d0] ? 0x8000 : 0));
+    }
   }
   // bonds
   std::vector<int> ll, hh, lh;
@@ -642,6 +701,8 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   CU_CHECK(cudaMemcpy(T.d_blob, blob.data(), o, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMalloc(&T.d_pair_seg, sizeof(uint16_t) * std::max<size_t>(pair_seg.size(), 1)));
   CU_CHECK(cudaMemcpy(T.d_pair_seg, pair_seg.data(), sizeof(uint16_t) * pair_seg.size(), cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMalloc(&T.d_pair_seg1, sizeof(uint16_t) * pair_seg1.size()));
+  CU_CHECK(cudaMemcpy(T.d_pair_seg1, pair_seg1.data(), sizeof(uint16_t) * pair_seg1.size(), cudaMemcpyHostToDevice));
   T.ok = true;
   return CMPY_OK;
 }
@@ -653,7 +714,7 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
 
 struct LongSet {            // all sub-rows whose dtop has the same popcount
   ClsTables cls;            // class-major tables of the 16-site sub-row sector
-  int pt = 0, ntop = 0, row_len = 0;
+  int pt = 0, ntop = 0, row_len = 0, shift = 0;
   uint32_t* d_top_val = nullptr;
   int* d_sub_off = nullptr;
   int* d_tb_ptr = nullptr;
@@ -684,13 +745,15 @@ static int upload_vec(T*& dptr, const std::vector<T>& v) {
   return CMPY_OK;
 }
 
+// `skipped` (optional): popcounts of the top bits whose sub-rows the class-major kernel cannot
+// take (odd length ...); without it such a sector makes the whole table set unavailable.
 static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                              const int* s1, const int* s2, int sign_width, const double* eps,
-                             i64 smem_optin) {
+                             i64 smem_optin, std::vector<int>* skipped = nullptr) {
   T.release();
   const u64* B = host_binom();
   const int R = LONG_RBITS, tb = num_sites - R;
-  if (tb < 1 || tb > 12 || n_dn < 0 || n_dn > num_sites) return CMPY_OK;
+  if (tb < 1 || tb > 16 || n_dn < 0 || n_dn > num_sites) return CMPY_OK;
   if ((i64)B[num_sites * BINOM_N + n_dn] != num_dn || num_dn >= (1ll << 31)) return CMPY_OK;
   const int ntopall = 1 << tb;
   // sub-row offsets in the ascending (natural) order of the dn strings
@@ -725,11 +788,27 @@ static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn,
     int rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
                               eps, smem_optin);
     if (rc) { S.release(); return rc; }
-    if (!S.cls.ok) { S.release(); T.release(); return CMPY_OK; }
+    if (!S.cls.ok) {
+      S.release();
+      if (skipped) { skipped->push_back(pt); continue; }
+      T.release();
+      return CMPY_OK;
+    }
     std::vector<uint32_t> top_val;
     for (int dt = 0; dt < ntopall; ++dt)
       if (__builtin_popcount(dt) == pt) top_val.push_back((uint32_t)dt);
     S.ntop = (int)top_val.size();
+    {  // 16-byte alignment of the sub-rows: all even (shift 0) or all odd (shift 1) element offsets
+      int n_odd = 0;
+      for (uint32_t dt : top_val) n_odd += (int)(sub_off[dt] & 1);
+      if (n_odd != 0 && n_odd != S.ntop) {
+        S.release();
+        if (skipped) { skipped->push_back(pt); continue; }
+        T.release();
+        return CMPY_OK;
+      }
+      S.shift = n_odd ? 1 : 0;
+    }
     std::vector<int> so(S.ntop), tb_ptr(S.ntop + 1, 0);
     std::vector<int2> tb_ent, sb_src((size_t)std::max(1, T.nsb) * S.ntop, make_int2(0, 0));
     for (int ti = 0; ti < S.ntop; ++ti) {

@@ -210,9 +210,9 @@ struct HubbardOp : cmpy_op_s {
   int launch_long(HubParams& p, cudaStream_t st) {
     for (auto& S : lng.sets) {
       ClsParams cp;
-      cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.cls.d_pair_seg;
+      cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
       cp.e_dn_const = lng.e_dn_const; cp.stagger_cycles = 0;
-      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb;
+      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb; cp.lg.shift = S.shift;
       cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
       cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
       i64 g = sm_count;

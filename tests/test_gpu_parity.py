@@ -865,3 +865,61 @@ def test_hv_long_rows(cm, L, nu, nd, nbfn, kw):
     sh = ShardedHubbardOperator(model, nu, nd, exchange="a2a")
     y = sh.apply_local(xt).cpu().numpy()
     assert relerr(y, ref) < HV_RTOL
+
+
+# ---------------------------------------------------------------------------------------
+# K5 on more than 16 sites: class-major fast path (variant 0 / 5) vs the generic row kernel (1)
+# ---------------------------------------------------------------------------------------
+
+class _LadderStandIn:
+    """2 x (N/2) ladder: site = 2*rung + leg."""
+
+    def __init__(self, num_sites):
+        self.num_sites = num_sites
+
+    def neighbors(self, i):
+        n = self.num_sites
+        out = [i ^ 1]
+        if i - 2 >= 0:
+            out.append(i - 2)
+        if i + 2 < n:
+            out.append(i + 2)
+        return out
+
+
+@pytest.mark.parametrize("N,s,latt,j,jz", [
+    (17, 0.5, "chain", 1.0, 1.0), (18, 0, "ring", 0.9, 1.1), (18, 1, "ladder", 1.0, 0.7),
+    (20, 0, "chain", 1.0, 1.0), (19, -1.5, "ring", 0.8, 1.3), (22, 3, "chain", 1.0, 0.5),
+])
+def test_heisenberg_fast_path(cm, N, s, latt, j, jz):
+    import torch
+    from cmpy_b200.models import HeisenbergModel
+    from cmpy_b200.exactdiag import lanczos_run
+    from refshim import ChainStandIn
+
+    lat = _LadderStandIn(N) if latt == "ladder" else ChainStandIn(N, periodic=(latt == "ring"))
+    model = HeisenbergModel(lat, j=j, jz=jz)
+    h = model.hamilton_operator(s=s)
+    n = h.shape[0]
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    x = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    h.set_variant(1)
+    ref = h.matvec(x)
+    d_ref = h.diagonal()
+    h.set_variant(5)            # raises if the fast path is not available
+    y = h.matvec(x)
+    assert float((y - ref).abs().max() / ref.abs().max()) < HV_RTOL
+    if n <= 200000:
+        st = orc.spin_states(N, s)
+        nbl = [list(lat.neighbors(i)) for i in range(N)]
+        r, c, v = orc.heisenberg_triplets(st, nbl, j, jz)
+        xo = x.cpu().numpy()
+        assert relerr(y.cpu().numpy(), orc.coo_matvec(len(st), r, c, v, xo)) < HV_RTOL
+    # fused Lanczos through the multi-launch operator
+    e = []
+    for variant in (1, 0):
+        h.set_variant(variant)
+        res = lanczos_run(h, None, maxit=500, tol=1e-12, resid_tol=1e-9)
+        e.append(res.e0)
+    assert abs(e[0] - e[1]) < E0_TOL
+    assert_allclose(h.diagonal(), d_ref, atol=1e-13)
