@@ -333,7 +333,7 @@ struct HeisenbergOp : cmpy_op_s {
     for (auto& S : lng.sets) {
       ClsParams cp;
       cp.hp = hp; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
-      cp.e_dn_const = 0.0; cp.stagger_cycles = 0; cp.sd = sd;
+      cp.e_dn_const = 0.0; cp.sd = sd;
       cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb; cp.lg.shift = S.shift;
       cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
       cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;

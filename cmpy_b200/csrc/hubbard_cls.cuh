@@ -98,7 +98,6 @@ struct ClsParams {
   const uint16_t* pair_seg;  // global: natural segment ordinal of the first valid column of pair i |
                              // (second column starts the next segment) << 15; one table per shift
   double e_dn_const;
-  int stagger_cycles;        // start delay of CTA b: (b % 3) * stagger_cycles (de-phases the SMs)
 };
 
 struct __align__(16) UpEnt2 { int off; int pad; double coef; };  // element offset relative to the row
@@ -282,10 +281,6 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
       if (d + 1 >= ndi) slot1 = slot0;
       slots[i] = (uint32_t)slot0 | ((uint32_t)slot1 << 16);
     }
-  }
-  if (cp.stagger_cycles > 0) {  // de-phase the SMs so that only a part of them gathers at a time
-    const long long t_end = clock64() + (long long)(blockIdx.x % 3) * cp.stagger_cycles;
-    while (clock64() < t_end) { }
   }
 #ifdef CLS_TIMING
   long long tph[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();

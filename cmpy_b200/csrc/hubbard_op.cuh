@@ -44,7 +44,6 @@ struct HubbardOp : cmpy_op_s {
   ClsTables cls;             // class-major two-phase kernel (uniform models, long rows)
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
-  int cls_stagger = 0;       // see ClsParams::stagger_cycles (env CMPY_CLS_STAGGER overrides)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
 
   ~HubbardOp() override {
@@ -194,7 +193,6 @@ struct HubbardOp : cmpy_op_s {
   int launch_cls(HubParams& p, cudaStream_t st) {
     ClsParams cp;
     cp.hp = p; cp.lay = cls.lay; cp.blob = cls.d_blob; cp.pair_seg = cls.d_pair_seg; cp.e_dn_const = cls.e_dn_const;
-    cp.stagger_cycles = p.with_up ? cls_stagger : 0;
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
@@ -211,7 +209,7 @@ struct HubbardOp : cmpy_op_s {
     for (auto& S : lng.sets) {
       ClsParams cp;
       cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
-      cp.e_dn_const = lng.e_dn_const; cp.stagger_cycles = 0;
+      cp.e_dn_const = lng.e_dn_const;
       cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb; cp.lg.shift = S.shift;
       cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
       cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
@@ -257,7 +255,6 @@ struct HubbardOp : cmpy_op_s {
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8>, 1024, cls.smem));
     if (nb < 1) { cls.ok = false; return CMPY_OK; }
     cls_default = dn.num >= 2048;  // long rows: one CTA per SM anyway
-    if (const char* e = getenv("CMPY_CLS_STAGGER")) cls_stagger = atoi(e);
     return CMPY_OK;
   }
 

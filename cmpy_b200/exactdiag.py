@@ -176,6 +176,7 @@ def gf_continued_fraction(model, z, pos=0, sigma=UP, n_up=None, n_dn=None, gs=No
     """Zero-temperature G_{pos,sigma}(z) = <gs|c 1/(z-(H-E0)) c^+|gs> + <gs|c^+ 1/(z+(H-E0)) c|gs>
     by Lanczos + continued fraction, entirely on the device.
 
+    ``pos`` is a site or a pair ``(i, j)`` (off-diagonal G_ij, use ``signed=True`` there).
     The ground state is searched in sector ``(n_up, n_dn)`` (default: half filling
     ``num_sites//2`` each).  ``signed=False`` uses the reference's signless ladder operators
     (cmpy/operators.py:652-703), so the result matches ``gf_lehmann`` in the T -> 0 limit."""
@@ -197,21 +198,35 @@ def gf_continued_fraction(model, z, pos=0, sigma=UP, n_up=None, n_dn=None, gs=No
     zt, zshape = _z_tensor(z)
     g = torch.zeros_like(zt)
     info = {"e0": e0, "norms": [0.0, 0.0], "nit": [0, 0]}
+    pair = isinstance(pos, (tuple, list))
+    if pair and pos[0] == pos[1]:
+        pos, pair = int(pos[0]), False
     for part, (sec_t, sign) in enumerate(((basis.upper_sector(n_up, n_dn, sigma), +1),
                                            (basis.lower_sector(n_up, n_dn, sigma), -1))):
         if sec_t is None:
             continue
         cls = CreationOperator if sign > 0 else AnnihilationOperator
-        phi = cls(sector, sec_t, pos=pos, sigma=sigma, signed=signed).apply(psi)
-        norm2 = float(torch.dot(phi, phi))
-        info["norms"][part] = norm2
-        if norm2 < 1e-28:
-            continue
-        ham_t = model.hamilton_operator(sector=sec_t)
-        m = min(num_coeffs, ham_t.shape[0])
-        res = lanczos_run(ham_t, phi, maxit=m, tol=0.0, resid_tol=0.0, check_every=50)
-        info["nit"][part] = res.nit
-        cf_eval(res.alpha, res.beta[1:res.nit], norm2, e0, zt, sign=sign, out=g)
+        ham_t = None
+        if pair:
+            # off-diagonal G_ij (reference sketch: lehmann_full.py:53-97) by
+            # polarisation: for real symmetric H and a real ground state
+            #   <T_i gs| R(z) |T_j gs> = ( <phi+|R|phi+> - <phi-|R|phi-> ) / 4,   phi+- = (T_i +- T_j)|gs>
+            pi_ = cls(sector, sec_t, pos=int(pos[0]), sigma=sigma, signed=signed).apply(psi)
+            pj_ = cls(sector, sec_t, pos=int(pos[1]), sigma=sigma, signed=signed).apply(psi)
+            starts = ((pi_ + pj_, 0.25), (pi_ - pj_, -0.25))
+        else:
+            starts = ((cls(sector, sec_t, pos=pos, sigma=sigma, signed=signed).apply(psi), 1.0),)
+        for phi, weight in starts:
+            norm2 = float(torch.dot(phi, phi))
+            info["norms"][part] += weight * norm2
+            if norm2 < 1e-28:
+                continue
+            if ham_t is None:
+                ham_t = model.hamilton_operator(sector=sec_t)
+            m = min(num_coeffs, ham_t.shape[0])
+            res = lanczos_run(ham_t, phi, maxit=m, tol=0.0, resid_tol=0.0, check_every=50)
+            info["nit"][part] = max(info["nit"][part], res.nit)
+            cf_eval(res.alpha, res.beta[1:res.nit], weight * norm2, e0, zt, sign=sign, out=g)
     out = g.cpu().numpy().reshape(zshape)
     return (out, info) if return_info else out
 

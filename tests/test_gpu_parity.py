@@ -923,3 +923,45 @@ def test_heisenberg_fast_path(cm, N, s, latt, j, jz):
         e.append(res.e0)
     assert abs(e[0] - e[1]) < E0_TOL
     assert_allclose(h.diagonal(), d_ref, atol=1e-13)
+
+
+def test_gf_offdiagonal_continued_fraction(cm):
+    """f-4: G_ij(z) by polarisation.  U=0: exactly [(z - h)^-1]_ij of the hopping matrix (every
+    hop sign matters); U=4: the dense Lehmann sum built from this package's own dense H and
+    signed ladder matrices."""
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.exactdiag import gf_continued_fraction
+
+    z = np.linspace(-5, 5, 301) + 0.1j
+    L = 6
+    nb = chain(L) + [[0, 5], [1, 4]]
+    model = HubbardModel(L, nb, inter=0.0, mu=0.0, hop=1.0)
+    h = np.zeros((L, L))
+    for a, b in nb:
+        h[a, b] = h[b, a] = 1.0
+    ginv = np.linalg.inv(z[:, None, None] * np.eye(L)[None] - h[None])
+    for i, j in [(0, 3), (2, 5), (1, 1)]:
+        g = gf_continued_fraction(model, z, pos=(i, j), n_up=3, n_dn=2, signed=True)
+        assert np.abs(g - ginv[:, i, j]).max() < GF_TOL
+    # interacting, against dense ED assembled from the same operators
+    L = 4
+    model = HubbardModel(L, chain(L, True), inter=4.0, mu=2.0, hop=1.0)
+    basis = model.basis
+    sec, sp1, sm1 = basis.get_sector(2, 2), basis.upper_sector(2, 2, cm.UP), basis.lower_sector(2, 2, cm.UP)
+    ev, vec = np.linalg.eigh(model.hamiltonian(sector=sec))
+    e0, gs = ev[0], vec[:, 0]
+    evp, vp = np.linalg.eigh(model.hamiltonian(sector=sp1))
+    evm, vm = np.linalg.eigh(model.hamiltonian(sector=sm1))
+
+    def cd(p):
+        return cm.CreationOperator(sec, sp1, p, cm.UP, signed=True).toarray().real
+
+    def c(p):
+        return cm.AnnihilationOperator(sec, sm1, p, cm.UP, signed=True).toarray().real
+
+    for i, j in [(0, 1), (0, 2), (1, 3)]:
+        ai, aj = vp.T @ (cd(i) @ gs), vp.T @ (cd(j) @ gs)
+        bi, bj = vm.T @ (c(i) @ gs), vm.T @ (c(j) @ gs)
+        ref = (ai * aj / (z[:, None] - evp[None, :] + e0)).sum(1) + (bi * bj / (z[:, None] + evm[None, :] - e0)).sum(1)
+        g = gf_continued_fraction(model, z, pos=(i, j), n_up=2, n_dn=2, gs=(e0, gs), signed=True)
+        assert np.abs(g - ref).max() < GF_TOL
