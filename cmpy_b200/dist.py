@@ -153,8 +153,22 @@ class ShardedHubbardOperator:
             raise ValueError("exchange must be 'peer' or 'a2a'")
         self.exchange = exchange
         if exchange == "peer":
-            self._init_peer()
-        else:
+            try:
+                self._init_peer()
+                ok = 1
+            except Exception as exc:  # no peer mapping on this box (no NVLink / no fabric handles)
+                import logging
+
+                logging.getLogger("cmpy").warning("peer-memory exchange unavailable (%s); using all-to-all", exc)
+                ok = 0
+            if self.world > 1:  # every rank must take the same path
+                torch = _lib.require_cuda()
+                flag = torch.tensor([ok], dtype=torch.int32, device=_lib.device())
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                ok = int(flag.item())
+            if not ok:
+                self.exchange = exchange = "a2a"
+        if exchange != "peer":
             self._send = backend.empty(max(p.local_size, p.local_size_t))
             self._recv = backend.empty(max(p.local_size, p.local_size_t))
             self._xt = backend.empty(p.local_size_t)
