@@ -33,7 +33,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["ShardPlan", "ShardedHubbardOperator", "CudaBackend", "lanczos_sharded"]
+__all__ = ["ShardPlan", "ShardedHubbardOperator", "CudaBackend", "lanczos_sharded",
+           "gf_continued_fraction_sharded"]
 
 
 class ShardPlan:
@@ -338,7 +339,8 @@ class ShardedHubbardOperator:
         return self._pinned_out
 
 
-def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, seed=0, callback=None):
+def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, seed=0, callback=None,
+                    want_vector=False, resid_tol=0.0):
     """Two-vector Lanczos on an up-string-sharded operator: every rank holds its slab of the two
     Lanczos vectors (plus the operator's XT / YT slabs: 4 slabs in total, which is what lets the
     20-site half-filled sector, 34.1 GB per slab on 8 GPUs, fit 180 GB of HBM).  alpha / beta are
@@ -347,7 +349,10 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
     Recurrence (same as the single-GPU kernel, ref cmpy/exactdiag.py:324-347 for the
     coefficients): w <- H v - beta_j w (w holds v_{j-1}); alpha_j = <v, w>; w -= alpha_j v;
     beta_{j+1} = |w|; w /= beta_{j+1}; swap.  Returns ``(e0, alpha, beta, nit, converged)``;
-    e0 = lowest Ritz value, converged when it moves by less than ``tol`` between two checks."""
+    e0 = lowest Ritz value, converged when it moves by less than ``tol`` between two checks (and,
+    with ``resid_tol > 0``, the Ritz residual estimate beta_m |s_m| is below ``resid_tol``).
+    ``want_vector``: a second pass of the same recurrence accumulates the Ritz vector (one more
+    slab); the return value then ends with the local slab of the normalised ground state."""
     import torch
     from scipy.linalg import eigvalsh_tridiagonal
 
@@ -369,15 +374,20 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
         return acc
 
     n = op.local_size
-    if v0_local is None:
-        dev = op.backend.empty(1).device
-        g = torch.Generator(device=dev)
-        g.manual_seed(int(seed) + 7919 * op.rank)
-        v = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
-    else:
-        v = v0_local.clone()
+
+    def start():
+        if v0_local is None:
+            dev = op.backend.empty(1).device
+            g = torch.Generator(device=dev)
+            g.manual_seed(int(seed) + 7919 * op.rank)
+            v_ = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+        else:
+            v_ = v0_local.clone()
+        v_.div_(torch.sqrt(allsum(dot(v_, v_))))
+        return v_
+
+    v = start()
     w = torch.zeros_like(v)
-    v.div_(torch.sqrt(allsum(dot(v, v))))
     alphas = torch.zeros(int(maxit), dtype=torch.float64, device=v.device)
     betas = torch.zeros(int(maxit), dtype=torch.float64, device=v.device)
     e_prev, e0, converged, nit = None, float("nan"), False, 0
@@ -394,17 +404,109 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
         last = nit == int(maxit)
         if nit % int(check_every) == 0 or last:
             ah, bh = alphas[:nit].cpu().numpy(), betas[:nit].cpu().numpy()
-            e0 = float(eigvalsh_tridiagonal(ah, bh[:nit - 1], select="i", select_range=(0, 0))[0]) \
-                if nit > 1 else float(ah[0])
+            resid = 0.0
+            if nit > 1:
+                if resid_tol > 0:
+                    from scipy.linalg import eigh_tridiagonal as _eight
+
+                    ev_, sv_ = _eight(ah, bh[:nit - 1], select="i", select_range=(0, 0))
+                    e0, resid = float(ev_[0]), float(bh[nit - 1] * abs(sv_[-1, 0]))
+                else:
+                    e0 = float(eigvalsh_tridiagonal(ah, bh[:nit - 1], select="i", select_range=(0, 0))[0])
+            else:
+                e0 = float(ah[0])
             if callback is not None:
                 callback(nit, e0)
             if bh[nit - 1] < 1e-14 * max(1.0, abs(e0)):   # invariant subspace: exact
                 converged = True
                 break
-            if e_prev is not None and abs(e0 - e_prev) < tol:
+            if e_prev is not None and abs(e0 - e_prev) < tol and (resid_tol <= 0 or resid <= resid_tol):
                 converged = True
                 break
             e_prev = e0
         w.div_(b)
         v, w = w, v
-    return e0, alphas[:nit].cpu().numpy(), betas[:nit].cpu().numpy(), nit, converged
+    ah, bh = alphas[:nit].cpu().numpy(), betas[:nit].cpu().numpy()
+    if not want_vector:
+        return e0, ah, bh, nit, converged
+    # second pass: psi = sum_j s_j v_j with s the lowest eigenvector of the Lanczos matrix
+    from scipy.linalg import eigh_tridiagonal
+
+    if nit > 1:
+        _, svec = eigh_tridiagonal(ah, bh[:nit - 1], select="i", select_range=(0, 0))
+        coef = svec[:, 0]
+    else:
+        coef = np.ones(1)
+    del v, w
+    v = start()
+    w = torch.zeros_like(v)
+    psi = torch.zeros_like(v)
+    for j in range(nit):
+        psi.add_(v, alpha=float(coef[j]))
+        if j + 1 == nit:
+            break
+        if j > 0:
+            w.mul_(-float(bh[j - 1]))
+        op.apply_local(v, out=w, accumulate=True)
+        w.add_(v, alpha=-float(ah[j]))
+        w.div_(float(bh[j]))
+        v, w = w, v
+    psi.div_(torch.sqrt(allsum(dot(psi, psi))))
+    return e0, ah, bh, nit, converged, psi
+
+
+def gf_continued_fraction_sharded(model, z, pos=0, n_up=None, n_dn=None, num_coeffs=600, tol=1e-12,
+                                  group=None, return_info=False):
+    """Zero-temperature G_{pos,DN}(z) on an up-string-sharded sector: sharded Lanczos ground state,
+    c^+_{pos,dn} / c_{pos,dn} applied slab-locally (a dn ladder operator does not move amplitudes
+    between up-rows), sharded Lanczos from the two start vectors, continued fraction on every rank.
+    Same convention as ``exactdiag.gf_continued_fraction(..., sigma=DN)`` (signless operators of the
+    reference, cmpy/operators.py:652-703; for n_up = n_dn it equals the sigma=UP function)."""
+    from .basis import DN, Sector
+    from .exactdiag import _z_tensor, cf_eval
+    from .operators import AnnihilationOperator, CreationOperator
+
+    torch = _lib.require_cuda()
+    basis = model.basis
+    L = basis.num_sites
+    n_up = L // 2 if n_up is None else n_up
+    n_dn = L // 2 if n_dn is None else n_dn
+    op = ShardedHubbardOperator(model, n_up, n_dn, group=group)
+    e0, _, _, nit0, conv, psi = lanczos_sharded(op, maxit=3000, tol=tol, check_every=10, want_vector=True,
+                                                resid_tol=1e-10)
+    r0, r1 = op.plan.rows()
+    full = basis.get_sector(n_up, n_dn)
+    up_slab = np.asarray(full.up_states)[r0:r1]
+    sec_slab = Sector(up_slab, np.asarray(full.dn_states), n_up, n_dn, L)
+    zt, zshape = _z_tensor(z)
+    g = torch.zeros_like(zt)
+    info = {"e0": e0, "gs_iterations": nit0, "gs_converged": bool(conv), "norms": [0.0, 0.0], "nit": [0, 0]}
+    del op
+    for part, (nd_t, sign, cls) in enumerate(((n_dn + 1, +1, CreationOperator), (n_dn - 1, -1, AnnihilationOperator))):
+        if nd_t < 0 or nd_t > L:
+            continue
+        sec_t = Sector(up_slab, np.asarray(basis.get_states(nd_t)), n_up, nd_t, L)
+        phi = cls(sec_slab, sec_t, pos=pos, sigma=DN).apply(psi)
+        nrm = torch.dot(phi, phi)
+        if op_world(group) > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(nrm, group=group)
+        norm2 = float(nrm)
+        info["norms"][part] = norm2
+        if norm2 < 1e-28:
+            continue
+        op_t = ShardedHubbardOperator(model, n_up, nd_t, group=group)
+        m = min(int(num_coeffs), op_t.shape[0])
+        _, al, be, nit, _ = lanczos_sharded(op_t, v0_local=phi, maxit=m, tol=0.0, check_every=m)
+        info["nit"][part] = nit
+        cf_eval(al, be[:nit - 1], norm2, e0, zt, sign=sign, out=g)
+        del op_t
+    out = g.cpu().numpy().reshape(zshape)
+    return (out, info) if return_info else out
+
+
+def op_world(group=None):
+    import torch.distributed as dist
+
+    return dist.get_world_size(group) if dist.is_initialized() else 1

@@ -101,6 +101,13 @@ def _worker(rank, world, port, L, nu, nd, ret):
         r, c, v = orc.hubbard_triplets(up, dn, L, nb, 4.0, -2.0, 1.0)
         e_ref = np.linalg.eigvalsh(orc.coo_dense(len(up) * len(dn), r, c, v))[0]
         ok = ok and conv and abs(e0 - e_ref) < 1e-9
+        # Ritz vector from the second pass: sharded residual |H psi - e0 psi|
+        e0b, _, _, _, _, psi = lanczos_sharded(op, maxit=300, tol=1e-12, check_every=5, want_vector=True)
+        hp = op.apply_local(psi)
+        res2 = torch.dot(hp - e0b * psi, hp - e0b * psi)
+        nrm2 = torch.dot(psi, psi)
+        dist.all_reduce(res2); dist.all_reduce(nrm2)
+        ok = ok and abs(float(nrm2) - 1.0) < 1e-10 and float(res2) ** 0.5 < 1e-5
         t = torch.tensor([1.0 if ok else 0.0])
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
