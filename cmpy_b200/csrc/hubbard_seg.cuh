@@ -150,12 +150,12 @@ __device__ __forceinline__ double seg_dn_part(
   return acc;
 }
 
-// NT = threads per CTA (512: <=128 regs, 8 gathers in flight per lane; 1024: <=64 regs, 4)
+// NT = threads per CTA (512: <=128 regs, 8 gathers in flight per lane; 896: <=73 regs, 5; 1024: <=64 regs, 4)
 
 // smem: [table blob][dn strings u32[nd_pad]][row of x: double[nd]]
 template <bool UNI, bool LZ, bool VEC2, int NT>
 __global__ void __launch_bounds__(NT, 1) hub_seg_kernel(SegParams sp) {
-  constexpr int SEG_UPG = NT <= 512 ? 8 : 4;
+  constexpr int SEG_UPG = NT <= 512 ? 8 : (NT <= 896 ? 5 : 4);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[32];
   __shared__ UpEnt s_up[ELL_MAX_BONDS];
