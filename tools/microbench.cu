@@ -88,6 +88,76 @@ __global__ void __launch_bounds__(NT, 1) gather_hint_kernel(const double* __rest
   }
 }
 
+// TMA-fed gather: the neighbour rows are pulled into a shared-memory ring by 1-D bulk copies
+// (cp.async.bulk, mbarrier complete_tx), NS stages of CH doubles; consumers add them from smem.
+// Question: does a deep, register-free pipeline beat the 8 x 16-byte LDG.128 in flight per thread?
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+               :: "r"(s_addr(bar)), "r"(parity) : "memory");
+}
+template <int NS, int CH>
+__global__ void __launch_bounds__(1024, 1) tma_gather_kernel(const double* __restrict__ x, double* __restrict__ y,
+                                                            const Tab* __restrict__ tab, int nu, int nd) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* ring = reinterpret_cast<double*>(smraw);
+  __shared__ uint64_t full[NS], empty[NS];
+  __shared__ Tab st;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_addr(&full[s])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_addr(&empty[s])), "r"(32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nchunk = (nd + CH - 1) / CH;
+  long long issued = 0, consumed = 0;   // item counters (identical sequence in every thread)
+  for (int u = blockIdx.x; u < nu; u += gridDim.x) {
+    __syncthreads();
+    if (tid < sizeof(Tab) / 4) ((int*)&st)[tid] = ((const int*)&tab[u])[tid];
+    __syncthreads();
+    const int cu = st.cnt;
+    const long long row_items = (long long)nchunk * cu;
+    long long prod = 0;   // items of this row already issued (thread 0)
+    for (int c = 0; c < nchunk; ++c) {
+      const int c0 = c * CH, len = min(CH, nd - c0);
+      double a0 = 0, a1 = 0;
+      for (int k = 0; k < cu; ++k) {
+        if (tid == 0) {  // keep the ring full: issue items of this row up to NS ahead of consumption
+          while (prod < row_items && issued - consumed < NS) {
+            const int pc = (int)(prod / cu), pk = (int)(prod % cu);
+            const int s = (int)(issued % NS);
+            const uint32_t ph = (uint32_t)((issued / NS) & 1);
+            if (issued >= NS) mbar_wait(&empty[s], ph ^ 1u);
+            const int pc0 = pc * CH, plen = min(CH, nd - pc0);
+            const uint32_t bytes = (uint32_t)plen * 8u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_addr(&full[s])), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(s_addr(ring + (size_t)s * CH)), "l"(x + (i64)st.tgt[pk] * nd + pc0), "r"(bytes), "r"(s_addr(&full[s])) : "memory");
+            ++issued; ++prod;
+          }
+        }
+        const int s = (int)(consumed % NS);
+        const uint32_t ph = (uint32_t)((consumed / NS) & 1);
+        mbar_wait(&full[s], ph);
+        const int d = 2 * tid;
+        if (d < len) {
+          const double2 v = *reinterpret_cast<const double2*>(ring + (size_t)s * CH + d);
+          a0 += st.sgn[k] * v.x; a1 += st.sgn[k] * v.y;
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_addr(&empty[s])) : "memory");
+        ++consumed;
+        if (tid != 0) { if (issued < consumed) issued = consumed; }  // only thread 0 tracks `issued` exactly
+      }
+      const int d = 2 * tid;
+      if (d < len) *reinterpret_cast<double2*>(y + (i64)u * nd + c0 + d) = make_double2(a0, a1);
+    }
+  }
+}
+
 // smem LDS.64 throughput: mode 0 contiguous, 1 odd stride (71), 2 random, 3 contiguous LDS.128
 __global__ void __launch_bounds__(1024, 1) smem_kernel(double* out, int mode, int iters, const int* __restrict__ perm) {
   extern __shared__ double xs[];
@@ -191,6 +261,18 @@ int main(int argc, char** argv) {
   report("gather natural rows + st.cs, 148x768 UPG12", timeit([&] { gather_hint_kernel<768, 12, 1><<<148, 768>>>(x, y, dtab, nu, nd); }, 5));
   report("gather chunk-major wc=2048, 148x1024 UPG8", timeit([&] { gather_kernel<1024, 8><<<148, 1024>>>(x, y, dtab, nu, nd, 2048, 1); }, 5));
   report("gather chunk-major wc=4096, 148x1024 UPG8", timeit([&] { gather_kernel<1024, 8><<<148, 1024>>>(x, y, dtab, nu, nd, 4096, 1); }, 5));
+  {
+    constexpr int NS = 12, CH = 2048;
+    const size_t smem = (size_t)NS * CH * 8;
+    CK(cudaFuncSetAttribute(tma_gather_kernel<NS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    report("gather via TMA bulk copies, 12 x 16 KB ring, 148x1024", timeit([&] { tma_gather_kernel<NS, CH><<<148, 1024, smem>>>(x, y, dtab, nu, nd); }, 5));
+  }
+  {
+    constexpr int NS = 24, CH = 1024;
+    const size_t smem = (size_t)NS * CH * 8;
+    CK(cudaFuncSetAttribute(tma_gather_kernel<NS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    report("gather via TMA bulk copies, 24 x 8 KB ring, 148x1024 (512 active)", timeit([&] { tma_gather_kernel<NS, CH><<<148, 1024, smem>>>(x, y, dtab, nu, nd); }, 5));
+  }
   for (int wc : {512}) {
     char nm[128];
     snprintf(nm, sizeof nm, "gather chunk-major wc=%d (L2 set %.0f MB), grid 1184 x128 UPG13", wc, 8.0 * nu * wc / 1e6);
