@@ -1,6 +1,7 @@
 // cmpy_b200.cu -- C ABI of libcmpy_b200.so (see include/cmpy_b200.h).
 // Single translation unit; build: cmpy_b200/csrc/Makefile (nvcc, sm_100a).
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "sector.cuh"
 #include "hubbard.cuh"
@@ -176,6 +177,10 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
   if (!rc && fixed_popcount)
     rc = op->configure_long(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (rc) { delete op; return rc; }
+  {  // engine of the default class-major launches (0 until engine 2 is measured on the target box)
+    const char* e = getenv("CMPY_CLS_ENGINE");
+    if (e && atoi(e) == 2) op->cls_engine = 2;
+  }
   *out = op;
   return CMPY_OK;
 }
@@ -259,7 +264,7 @@ API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_
 }
 
 API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
-  ARG_CHECK(op && variant >= 0 && variant <= 8, "bad variant");
+  ARG_CHECK(op && variant >= 0 && variant <= 10, "bad variant");
   op->variant = variant;
   return CMPY_OK;
 }

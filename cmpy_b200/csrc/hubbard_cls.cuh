@@ -26,9 +26,12 @@
 // Measured on B200 (tools/microbench.cu): odd-stride LDS.64 = contiguous LDS.64 = 15.8
 // doubles/clk/SM, random LDS.64 = 5.2; whole-row gathers top out at ~8.5-9 TB/s of L2->SM traffic.
 #pragma once
+#include <algorithm>
+#include <string.h>
 #include "hubbard_seg.cuh"
 
 #define CLS_MAX_CLS 12
+#define CLS2_PIECES 32   // engine 2: work pieces per phase (= warps of a 1024-thread CTA)
 #define CLS_ZREG 96  // zero region appended to xs (target of HH list padding)
 
 struct ClsLayout {
@@ -53,8 +56,23 @@ struct ClsLayout {
   int off_lh_hi;     // u16 [nlh][nhi]     sbase of segment dh^bit | par << 14 | bit << 15
   int off_lh_lo;     // u8  [nlh][2][nq]   per value of the dh bit: r' | par << 7, or the slack slot
   int off_seg_delta; // i16 [nseg + 1]     (sbase - goff) of the segments in natural order
+  // ---- engine 2 (chunked tasks, hoisted per-lane state; see cls2_phase_a / cls2_phase_b) ----
+  int eng;           // 0: one (k, r) / dh item per warp pass; 2: chunked tasks
+  int zbase;         // first slot of the zero region (= xs_elems)
+  int nta, ntb;      // phase-A / phase-B task counts
+  int off_task_a;    // u32 [nta]  k | r0 << 8 | nr << 16   (nr consecutive ranks r of class k)
+  int off_task_b;    // u32 [ntb]  k | jj0 << 8 | njj << 16 (njj consecutive segments of class k)
+  int off_hhp_cm;    // u32 [nseg] HH list pointer of the segments in class-major order
+  int off_lhj;       // u32 [nlh][nseg] per class-major segment: slot of the source segment when the
+                     //     dl bit is clear (bits 0-13) / set (bits 14-27), the zero region when the
+                     //     hop is not allowed for that value; bit 31 = parity of the dh part
+  int off_lhq;       // u16 [nlh][nq]   per (k, r): r' | parity of the dl part << 7 | dl bit << 8 |
+                     //     source class exists << 9
+  uint16_t ptr_a[CLS2_PIECES + 1], ptr_b[CLS2_PIECES + 1];  // tasks of piece i: [ptr[i], ptr[i+1])
   int bytes;
 };
+
+#define CLS2_MAX_LH 4   // LH bonds whose per-lane entries engine 2 keeps in registers
 
 // Long rows (more than 16 sites): the dn string is (dtop, drest), drest = low 16 bits.  For a
 // fixed dtop the strings are contiguous in the row (a "sub-row" of C(16, n_dn - popc(dtop))
@@ -106,9 +124,33 @@ struct __align__(16) UpEnt2 { int off; int pad; double coef; };  // element offs
 // difference is the signed sum: a pair of the '+' part does p += x[e0]; n -= x[e1], a pair of
 // the '-' part does n += x[e0]; p -= x[e1]; odd-length parts are padded with a slot holding 0.
 
+// The phase bodies are __host__ __device__ so that tests/emu/cls_emu.cu can run them lane by lane
+// on the CPU against the oracle (no CUDA-only intrinsics outside these two helpers).
+#define CLS_HD __host__ __device__ __forceinline__
+CLS_HD int cls_popc(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+// v with its IEEE sign bit flipped when signmask = 0x80000000 (0: unchanged)
+CLS_HD double cls_flip(double v, uint32_t signmask) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double(__double2hiint(v) ^ (int)signmask, __double2loint(v));
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  b ^= (unsigned long long)signmask << 32;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+CLS_HD int cls_min(int a, int b) { return a < b ? a : b; }
+
 // ---- phase A body: one (k, r) pair, T blocks of 32 dh-segments (lanes along jj) ----
 template <int T, bool SPIN>
-__device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const SpinDiag& sd,
+CLS_HD void cls_phase_a(const ClsLayout& L, const SpinDiag& sd,
                                             const double* __restrict__ xs,
                                             double* __restrict__ ys, const uint8_t* __restrict__ ll_ent,
                                             const uint16_t* __restrict__ dh_list, uint32_t pp, int k,
@@ -117,7 +159,7 @@ __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const SpinDiag& 
   const int hk = L.H[k], pk = L.P[k], xb = L.xbase[k];
   int o[T];  // element offset of (jj, r = 0); lanes past the class recompute its last segment
 #pragma unroll
-  for (int t = 0; t < T; ++t) o[t] = xb + min(lane + 32 * t, hk - 1) * pk;
+  for (int t = 0; t < T; ++t) o[t] = xb + cls_min(lane + 32 * t, hk - 1) * pk;
   double ap[T], an[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
@@ -149,10 +191,10 @@ __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const SpinDiag& 
       if (SPIN) {  // ups carries the top bits of the spin string (dtop << 16)
         const uint32_t sfull = ups | dns;
         int cnt = 0;
-        for (int i = 0; i < sd.ndelta; ++i) cnt += __popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
+        for (int i = 0; i < sd.ndelta; ++i) cnt += cls_popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
         diag = sd.e0 + sd.escale * (double)cnt;
       } else {
-        diag = eu + u0 * (double)__popc(ups & dns);
+        diag = eu + u0 * (double)cls_popc(ups & dns);
       }
       ys[o[t] + r] = diag * xs[o[t] + r] + hop0 * (ap[t] - an[t]);
     }
@@ -162,7 +204,7 @@ __device__ __forceinline__ void cls_phase_a(const ClsLayout& L, const SpinDiag& 
 // ---- phase B body: one segment dh, T blocks of 32 ranks (lanes along r) ----
 // Lanes past the end of the segment read the following slots (inside xs) and are never stored.
 template <int T>
-__device__ __forceinline__ void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
+CLS_HD void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
                                             double* __restrict__ ys, const uint16_t* __restrict__ hh_ent,
                                             const uint16_t* __restrict__ lh_hi,
                                             const uint8_t* __restrict__ lh_lo, uint32_t pp, int k,
@@ -203,8 +245,7 @@ __device__ __forceinline__ void cls_phase_b(const ClsLayout& L, const double* __
       // table rows are nq long and r < 96 <= slack after the last class: in bounds for every lane
       const uint32_t lo = lo_tab[32 * t];
       const double v = xh[lo & 0x7fu];
-      const int vh = __double2hiint(v) ^ (int)(((lo << 24) ^ par_hi) & 0x80000000u);
-      hp[t] += __hiloint2double(vh, __double2loint(v));
+      hp[t] += cls_flip(v, ((lo << 24) ^ par_hi) & 0x80000000u);
     }
   }
   double* __restrict__ yp0 = ys + sb + lane;
@@ -213,13 +254,173 @@ __device__ __forceinline__ void cls_phase_b(const ClsLayout& L, const double* __
     if (lane + 32 * t < sk) yp0[32 * t] += hop0 * (hp[t] - hn[t]);
 }
 
+// ---------------------------------------------------------------------------------
+// Engine 2: the same class-major layout and hop lists, walked in chunked tasks so that
+// everything that depends on the lane only is computed once per task instead of once per
+// (k, r) / dh item:
+//   phase A  task = nr consecutive ranks r of one class k, lanes along jj.  Hoisted per lane:
+//            slot offsets, popcount of the dh part (diagonal), and the LH source segments
+//            (lhj).  LL hops as in engine 0.  The LH hops move here from phase B: for a fixed
+//            (k, r) the source rank r', the dl bit and the dl parity are warp-uniform (lhq),
+//            the source segment is the hoisted per-lane entry -> x[src + r'] is an odd-pitch
+//            (conflict-free) access and bonds whose source class does not exist are skipped
+//            for the whole warp.
+//   phase B  task = njj consecutive segments of one class, lanes along r: HH hops only.
+// ---------------------------------------------------------------------------------
+template <int T, bool SPIN>
+CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* __restrict__ tab,
+                         const double* __restrict__ xs, double* __restrict__ ys, uint32_t task,
+                         uint32_t ups, double eu, double u0, double hop0, int lane) {
+  const int k = (int)(task & 0xffu), r0 = (int)((task >> 8) & 0xffu), nr = (int)(task >> 16);
+  const int hk = L.H[k], pk = L.P[k], xb = L.xbase[k], nlh = L.nlh;
+  const uint8_t* __restrict__ ll_ent = tab + L.off_ll_ent;
+  const uint32_t* __restrict__ ll_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_ll_ptr) + L.qoff[k];
+  const uint16_t* __restrict__ dl_of_q = reinterpret_cast<const uint16_t*>(tab + L.off_dl_of_q) + L.qoff[k];
+  const uint16_t* __restrict__ dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list) + L.hoff[k];
+  const uint32_t* __restrict__ lhj = reinterpret_cast<const uint32_t*>(tab + L.off_lhj) + L.hoff[k];
+  const uint16_t* __restrict__ lhq = reinterpret_cast<const uint16_t*>(tab + L.off_lhq) + L.qoff[k];
+  int o[T];             // element offset of (jj, r = 0); lanes past the class recompute its last segment
+  uint32_t dhs[T];      // dh bits of the lane's segments, already shifted to their place in the string
+  uint32_t lh[CLS2_MAX_LH][T];
+  int ph[T];            // popcount of (ups & dh part)
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int jj = cls_min(lane + 32 * t, hk - 1);
+    o[t] = xb + jj * pk;
+    dhs[t] = (uint32_t)dh_list[jj] << L.m;
+    ph[t] = SPIN ? 0 : cls_popc(ups & dhs[t]);
+#pragma unroll
+    for (int b = 0; b < CLS2_MAX_LH; ++b) lh[b][t] = b < nlh ? lhj[b * L.nseg + jj] : 0u;
+  }
+#pragma unroll 1
+  for (int r = r0; r < r0 + nr; ++r) {
+    double ap[T], an[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
+    {  // LL hops: one list per (k, r), '+' pairs then '-' pairs
+      const uint32_t pp = ll_ptr[r];
+      const uint16_t* ent2 = reinterpret_cast<const uint16_t*>(ll_ent + (pp & 0xffffu));
+      const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
+      int i = 0;
+#pragma unroll 1
+      for (; i < npos; ++i) {
+        const uint32_t e = ent2[i];
+        const double* __restrict__ q0 = xs + (e & 0xffu);
+        const double* __restrict__ q1 = xs + (e >> 8);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { ap[t] += q0[o[t]]; an[t] -= q1[o[t]]; }
+      }
+#pragma unroll 1
+      for (; i < ntot; ++i) {
+        const uint32_t e = ent2[i];
+        const double* __restrict__ q0 = xs + (e & 0xffu);
+        const double* __restrict__ q1 = xs + (e >> 8);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { an[t] += q0[o[t]]; ap[t] -= q1[o[t]]; }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < CLS2_MAX_LH; ++b) {  // LH hops
+      if (b < nlh) {
+        const uint32_t w = lhq[b * L.nq + r];
+        if (w & 0x200u) {
+          const double* __restrict__ xq = xs + (w & 0x7fu);
+          const int sh = (w & 0x100u) ? 14 : 0;
+          const uint32_t sgn = (w & 0x80u) << 24;   // parity of the dl part -> sign bit position
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const uint32_t e = lh[b][t];
+            ap[t] += cls_flip(xq[(e >> sh) & 0x3fffu], (e ^ sgn) & 0x80000000u);
+          }
+        }
+      }
+    }
+    const uint32_t dlbits = dl_of_q[r];
+    const int pl = SPIN ? 0 : cls_popc(ups & dlbits);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (lane + 32 * t < hk) {
+        double diag;
+        if (SPIN) {  // ups carries the top bits of the spin string (dtop << 16)
+          const uint32_t sfull = ups | dhs[t] | dlbits;
+          int cnt = 0;
+          for (int i = 0; i < sd.ndelta; ++i) cnt += cls_popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
+          diag = sd.e0 + sd.escale * (double)cnt;
+        } else {
+          diag = eu + u0 * (double)(ph[t] + pl);
+        }
+        ys[o[t] + r] = diag * xs[o[t] + r] + hop0 * (ap[t] - an[t]);
+      }
+    }
+  }
+}
+
+template <int T>
+CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ tab,
+                         const double* __restrict__ xs, double* __restrict__ ys, uint32_t task,
+                         double hop0, int lane) {
+  const int k = (int)(task & 0xffu), jj0 = (int)((task >> 8) & 0xffu), njj = (int)(task >> 16);
+  const int sk = L.S[k], pk = L.P[k];
+  const uint32_t* __restrict__ hhp = reinterpret_cast<const uint32_t*>(tab + L.off_hhp_cm) + L.hoff[k];
+  const uint16_t* __restrict__ hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
+  const double* __restrict__ xp0 = xs + lane;
+#pragma unroll 1
+  for (int jj = jj0; jj < jj0 + njj; ++jj) {
+    const uint32_t pp = hhp[jj];
+    const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
+    if (ntot == 0) continue;
+    double hp[T], hn[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { hp[t] = 0.0; hn[t] = 0.0; }
+    const uint32_t* ent2 = reinterpret_cast<const uint32_t*>(hh_ent + (pp & 0xffffu));
+    int i = 0;
+#pragma unroll 1
+    for (; i < npos; ++i) {
+      const uint32_t e = ent2[i];
+      const double* __restrict__ q0 = xp0 + (e & 0xffffu);
+      const double* __restrict__ q1 = xp0 + (e >> 16);
+#pragma unroll
+      for (int t = 0; t < T; ++t) { hp[t] += q0[32 * t]; hn[t] -= q1[32 * t]; }
+    }
+#pragma unroll 1
+    for (; i < ntot; ++i) {
+      const uint32_t e = ent2[i];
+      const double* __restrict__ q0 = xp0 + (e & 0xffffu);
+      const double* __restrict__ q1 = xp0 + (e >> 16);
+#pragma unroll
+      for (int t = 0; t < T; ++t) { hn[t] += q0[32 * t]; hp[t] -= q1[32 * t]; }
+    }
+    double* __restrict__ yp0 = ys + L.xbase[k] + jj * pk + lane;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (lane + 32 * t < sk) yp0[32 * t] += hop0 * (hp[t] - hn[t]);
+  }
+}
+
+// warp-level dispatch on the number of 32-lane blocks (classes are at most 96 long / high)
+template <bool SPIN>
+CLS_HD void cls2_task_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* tab, const double* xs,
+                        double* ys, uint32_t task, uint32_t ups, double eu, double u0, double hop0, int lane) {
+  const int hk = L.H[task & 0xffu];
+  if (hk <= 32) cls2_phase_a<1, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
+  else if (hk <= 64) cls2_phase_a<2, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
+  else cls2_phase_a<3, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
+}
+CLS_HD void cls2_task_b(const ClsLayout& L, const unsigned char* tab, const double* xs, double* ys,
+                        uint32_t task, double hop0, int lane) {
+  const int sk = L.S[task & 0xffu];
+  if (sk <= 32) cls2_phase_b<1>(L, tab, xs, ys, task, hop0, lane);
+  else if (sk <= 64) cls2_phase_b<2>(L, tab, xs, ys, task, hop0, lane);
+  else cls2_phase_b<3>(L, tab, xs, ys, task, hop0, lane);
+}
+
 __device__ __forceinline__ int seg_delta_g(const ClsParams& cp, int si) {
   return (int)reinterpret_cast<const int16_t*>(cp.blob + cp.lay.off_seg_delta)[si];
 }
 
 // smem: [table blob][xs: xs_elems + CLS_ZREG doubles][ys: xs_elems doubles]
 // UPG = 0 compiles the up-hop gathers out (row-slab launches of the sharded operator).
-template <bool LZ, int NT, int UPG_, bool LONG = false, bool SPIN = false>
+template <bool LZ, int NT, int UPG_, bool LONG = false, bool SPIN = false, int ENG = 0>
 __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   constexpr bool WITH_UP = UPG_ > 0;
   constexpr int UPG = WITH_UP ? UPG_ : 1;
@@ -348,6 +549,12 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + b));
     }
     // ---- phase A: lanes along jj, LL hops + diagonal -> ys ----
+    if (ENG == 2) {
+      const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
+      for (int pc = warp; pc < CLS2_PIECES; pc += NW)
+        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
+          cls2_task_a<SPIN>(L, cp.sd, tab, xs, ys, task_a[it], ups, eu, u0, hop0, lane);
+    } else
     for (int it = warp; it < L.na; it += NW) {
       const int q = item_a[it];
       const int k = k_of_q[q];
@@ -362,6 +569,11 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
     __syncthreads();
     CLS_TICK(2)
     // ---- phase B: lanes along r, HH + LH hops accumulated into ys ----
+    if (ENG == 2) {
+      const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
+      for (int pc = warp; pc < CLS2_PIECES; pc += NW)
+        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it) cls2_task_b(L, tab, xs, ys, task_b[it], hop0, lane);
+    } else
     for (int it = warp; it < L.nb; it += NW) {
       const int dh = item_b[it];
       const int k = hi_k[dh];
@@ -479,9 +691,20 @@ struct ClsTables {
 // Builds the class-major tables for the dn species.  ok=false (no error) when the sector is
 // outside what the kernel supports (non-sector string list, odd row length, row too long for
 // shared memory, classes longer than 96).
-static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
-                            const int* s1, const int* s2, int sign_width, const double* eps,
-                            i64 smem_optin) {
+// Host-only part (no CUDA calls): layout, table blob and the column-pair maps.  eng selects the
+// table set: 0 = per-item phases (cls_phase_a / cls_phase_b), 2 = chunked tasks (cls2_*).
+struct ClsHost {
+  ClsLayout lay;
+  std::vector<unsigned char> blob;
+  std::vector<uint16_t> pair_seg, pair_seg1;
+  bool ok = false;
+  double e_dn_const = 0.0;
+  size_t smem = 0;
+};
+
+static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
+                          const int* s1, const int* s2, int sign_width, const double* eps,
+                          i64 smem_optin, int eng = 0) {
   T.ok = false;
   const u64* B = host_binom();
   if (n_dn < 0 || n_dn > num_sites || num_sites < 2) return CMPY_OK;
@@ -525,7 +748,10 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
   }
   std::vector<int> hi_k(nhi, 0xff), hi_goff(nhi, 0), hi_sbase(nhi, 0), dh_list(std::max(nseg, 1), 0);
   std::vector<int> seg_delta;  // natural order
-  std::vector<uint16_t> pair_seg((size_t)num_dn / 2, 0), pair_seg1((size_t)num_dn / 2 + 1, 0);
+  std::vector<uint16_t>& pair_seg = T.pair_seg;
+  std::vector<uint16_t>& pair_seg1 = T.pair_seg1;
+  pair_seg.assign((size_t)num_dn / 2, 0);
+  pair_seg1.assign((size_t)num_dn / 2 + 1, 0);
   std::vector<int> seg_of((size_t)num_dn, 0);
   {
     std::vector<int> fill(m + 1, 0);
@@ -649,55 +875,184 @@ static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, i
     if (hi_k[dh] != 0xff) item_b.push_back((uint16_t)dh);
   L.na = (int)item_a.size();
   L.nb = (int)item_b.size();
+  L.eng = eng;
+  L.zbase = zbase;
+  // ---- engine 2: chunked tasks, class-major HH pointers, LH tables split into a per-lane part
+  //      (lhj, indexed by the class-major segment) and a warp-uniform part (lhq, indexed by (k, r)) ----
+  std::vector<uint32_t> task_a, task_b, hhp_cm, lhj;
+  std::vector<uint16_t> lhq;
+  if (eng == 2) {
+    if (L.nlh > CLS2_MAX_LH || m > 8 || hb > 8) return CMPY_OK;  // task fields are 8 bits wide
+    // The (k, r) columns of phase A / (k, jj) segments of phase B, in class-major order, are cut
+    // into CLS2_PIECES contiguous pieces of about equal estimated cost (32-lane blocks x list
+    // entries); a piece that spans a class boundary becomes several tasks.  Warp w of the CTA
+    // takes the pieces w, w + NW, ... -- with 32 warps exactly one piece each, so the per-lane
+    // state is set up once or twice per row and the warps finish together.
+    auto partition = [&](std::vector<uint32_t>& out, std::vector<uint16_t>& ptr, const int* lanes_dim,
+                         const int* loop_dim, auto&& cost) {
+      double total = 0.0;
+      for (int k = 0; k <= m; ++k)
+        if (L.H[k] > 0)
+          for (int c = 0; c < loop_dim[k]; ++c) total += ((lanes_dim[k] + 31) / 32) * cost(k, c);
+      out.clear();
+      ptr.assign(CLS2_PIECES + 1, 0);
+      double acc = 0.0;
+      int piece = 0, cur_k = -1, c0 = 0, n = 0;
+      auto flush = [&]() {
+        if (n > 0) out.push_back((uint32_t)cur_k | ((uint32_t)c0 << 8) | ((uint32_t)n << 16));
+        n = 0;
+      };
+      for (int k = 0; k <= m; ++k) {
+        if (L.H[k] <= 0) continue;
+        for (int c = 0; c < loop_dim[k]; ++c) {
+          const double w = ((lanes_dim[k] + 31) / 32) * cost(k, c);
+          // close the piece when its share of the total is used up (never leave a piece empty
+          // while work remains, never open more than CLS2_PIECES pieces)
+          if (piece + 1 < CLS2_PIECES && acc + 0.5 * w > total * (piece + 1) / CLS2_PIECES && (n > 0 || (int)out.size() > ptr[piece])) {
+            flush();
+            ptr[++piece] = (uint16_t)out.size();
+          }
+          if (n > 0 && cur_k != k) flush();
+          if (n == 0) { cur_k = k; c0 = c; }
+          ++n;
+          acc += w;
+        }
+      }
+      flush();
+      while (piece < CLS2_PIECES) ptr[++piece] = (uint16_t)out.size();
+    };
+    std::vector<uint16_t> ptr_a, ptr_b;
+    auto cost_a = [&](int k, int r) {
+      const uint32_t pp = ll_ptr[L.qoff[k] + r];
+      return 2.0 * (double)(pp >> 24) + (double)L.nlh + 2.0;
+    };
+    auto cost_b = [&](int k, int jj) {
+      const uint32_t pp = hh_ptr[dh_list[L.hoff[k] + jj]];
+      return 2.0 * (double)(pp >> 24) + 1.0;
+    };
+    partition(task_a, ptr_a, L.H, L.S, cost_a);   // lanes along jj (H_k), loop over r (S_k)
+    partition(task_b, ptr_b, L.S, L.H, cost_b);   // lanes along r (S_k), loop over jj (H_k)
+    L.nta = (int)task_a.size();
+    L.ntb = (int)task_b.size();
+    for (int i = 0; i <= CLS2_PIECES; ++i) { L.ptr_a[i] = ptr_a[i]; L.ptr_b[i] = ptr_b[i]; }
+    hhp_cm.assign(std::max(nseg, 1), 0);
+    for (int sgi = 0; sgi < nseg; ++sgi) hhp_cm[sgi] = hh_ptr[dh_list[sgi]];
+    lhj.assign((size_t)std::max(1, L.nlh) * std::max(nseg, 1), 0);
+    lhq.assign((size_t)std::max(1, L.nlh) * nlo, 0);
+    for (int qb = 0; qb < L.nlh; ++qb) {
+      const int b = lh[qb];
+      const int a = s1[b], c = s2[b] - m;  // a inside dl, c inside dh
+      for (int sgi = 0; sgi < nseg; ++sgi) {
+        const int dh = dh_list[sgi];
+        const int nh = dh ^ (1 << c);
+        const int bit = (dh >> c) & 1;
+        const uint32_t par = (uint32_t)parity((u64)dh << m, m - 1, s2[b]);  // bits of dh strictly below c
+        const uint32_t src = (hi_k[nh] != 0xff) ? (uint32_t)hi_sbase[nh] : (uint32_t)zbase;
+        // dl bit clear: the particle sits on c in dh (bit = 1) and the source has it on a
+        const uint32_t off_clear = bit ? src : (uint32_t)zbase;
+        const uint32_t off_set = bit ? (uint32_t)zbase : src;
+        lhj[(size_t)qb * nseg + sgi] = off_clear | (off_set << 14) | (par << 31);
+      }
+      for (int q = 0; q < nlo; ++q) {
+        const int dl = dl_of_q[q], k = k_of_q[q];
+        const int bit_lo = (dl >> a) & 1;
+        const int kp = k + (bit_lo ? -1 : 1);  // class of the source segment
+        uint16_t e = 0;
+        if (kp >= 0 && kp <= m && L.H[kp] > 0 && L.H[k] > 0) {
+          const int nl = dl ^ (1 << a);
+          const int par = parity((u64)dl, a, m);  // bits of dl strictly above a
+          e = (uint16_t)(lo_rank[nl] | (par << 7) | (bit_lo << 8) | (1 << 9));
+        }
+        lhq[(size_t)qb * nlo + q] = e;
+      }
+    }
+  }
   // energies: eps uniform -> eps * n_dn summed like weighted_element (ascending adds)
   { double v = 0; for (int i = 0; i < n_dn; ++i) v += eps[0]; T.e_dn_const = v; }
   // blob layout
   int o = 0;
   auto place = [&](int& off, size_t bytes) { off = o; o = align16(o + (int)std::max<size_t>(bytes, 16)); };
-  place(L.off_item_a, 2 * item_a.size());
-  place(L.off_item_b, 2 * item_b.size());
-  place(L.off_k_of_q, nlo);
-  place(L.off_dl_of_q, 2 * nlo);
-  place(L.off_ll_ptr, 4 * nlo);
-  place(L.off_ll_ent, ll_ent.size());
-  place(L.off_dh_list, 2 * dh_list.size());
-  place(L.off_hi_goff, 2 * nhi);
-  place(L.off_hi_sbase, 2 * nhi);
-  place(L.off_hi_k, nhi);
-  place(L.off_hh_ptr, 4 * nhi);
-  place(L.off_hh_ent, 2 * hh_ent.size());
-  place(L.off_lh_hi, 2 * lh_hi.size());
-  place(L.off_lh_lo, lh_lo.size());
-  place(L.off_seg_delta, 2 * seg_delta.size());
+  if (eng == 2) {
+    place(L.off_task_a, 4 * task_a.size());
+    place(L.off_task_b, 4 * task_b.size());
+    place(L.off_dl_of_q, 2 * nlo);
+    place(L.off_ll_ptr, 4 * nlo);
+    place(L.off_ll_ent, ll_ent.size());
+    place(L.off_dh_list, 2 * dh_list.size());
+    place(L.off_hhp_cm, 4 * hhp_cm.size());
+    place(L.off_hh_ent, 2 * hh_ent.size());
+    place(L.off_lhj, 4 * lhj.size());
+    place(L.off_lhq, 2 * lhq.size());
+    place(L.off_seg_delta, 2 * seg_delta.size());
+  } else {
+    place(L.off_item_a, 2 * item_a.size());
+    place(L.off_item_b, 2 * item_b.size());
+    place(L.off_k_of_q, nlo);
+    place(L.off_dl_of_q, 2 * nlo);
+    place(L.off_ll_ptr, 4 * nlo);
+    place(L.off_ll_ent, ll_ent.size());
+    place(L.off_dh_list, 2 * dh_list.size());
+    place(L.off_hi_goff, 2 * nhi);
+    place(L.off_hi_sbase, 2 * nhi);
+    place(L.off_hi_k, nhi);
+    place(L.off_hh_ptr, 4 * nhi);
+    place(L.off_hh_ent, 2 * hh_ent.size());
+    place(L.off_lh_hi, 2 * lh_hi.size());
+    place(L.off_lh_lo, lh_lo.size());
+    place(L.off_seg_delta, 2 * seg_delta.size());
+  }
   L.bytes = o;
   const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
   T.smem = (size_t)L.bytes + sizeof(double) * ((size_t)xs_total + (size_t)L.xs_elems);
   if (T.smem + 2560 > (size_t)smem_optin) return CMPY_OK;  // + static smem of the kernel
-  std::vector<unsigned char> blob(o, 0);
+  std::vector<unsigned char>& blob = T.blob;
+  blob.assign(o, 0);
   auto put = [&](int off, const void* src, size_t bytes) { if (bytes) memcpy(&blob[off], src, bytes); };
   auto narrow16 = [](const std::vector<int>& v) { std::vector<uint16_t> t(v.size()); for (size_t i = 0; i < v.size(); ++i) t[i] = (uint16_t)v[i]; return t; };
   auto narrow8 = [](const std::vector<int>& v) { std::vector<uint8_t> t(v.size()); for (size_t i = 0; i < v.size(); ++i) t[i] = (uint8_t)v[i]; return t; };
-  put(L.off_item_a, item_a.data(), 2 * item_a.size());
-  put(L.off_item_b, item_b.data(), 2 * item_b.size());
-  { auto t = narrow8(k_of_q); put(L.off_k_of_q, t.data(), t.size()); }
   { auto t = narrow16(dl_of_q); put(L.off_dl_of_q, t.data(), 2 * t.size()); }
   put(L.off_ll_ptr, ll_ptr.data(), 4 * ll_ptr.size());
   put(L.off_ll_ent, ll_ent.data(), ll_ent.size());
   { auto t = narrow16(dh_list); put(L.off_dh_list, t.data(), 2 * t.size()); }
-  { auto t = narrow16(hi_goff); put(L.off_hi_goff, t.data(), 2 * t.size()); }
-  { auto t = narrow16(hi_sbase); put(L.off_hi_sbase, t.data(), 2 * t.size()); }
-  { auto t = narrow8(hi_k); put(L.off_hi_k, t.data(), t.size()); }
-  put(L.off_hh_ptr, hh_ptr.data(), 4 * hh_ptr.size());
   put(L.off_hh_ent, hh_ent.data(), 2 * hh_ent.size());
-  put(L.off_lh_hi, lh_hi.data(), 2 * lh_hi.size());
-  put(L.off_lh_lo, lh_lo.data(), lh_lo.size());
   { std::vector<int16_t> t(seg_delta.size()); for (size_t i = 0; i < t.size(); ++i) t[i] = (int16_t)seg_delta[i]; put(L.off_seg_delta, t.data(), 2 * t.size()); }
-  CU_CHECK(cudaMalloc(&T.d_blob, o));
-  CU_CHECK(cudaMemcpy(T.d_blob, blob.data(), o, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMalloc(&T.d_pair_seg, sizeof(uint16_t) * std::max<size_t>(pair_seg.size(), 1)));
-  CU_CHECK(cudaMemcpy(T.d_pair_seg, pair_seg.data(), sizeof(uint16_t) * pair_seg.size(), cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMalloc(&T.d_pair_seg1, sizeof(uint16_t) * pair_seg1.size()));
-  CU_CHECK(cudaMemcpy(T.d_pair_seg1, pair_seg1.data(), sizeof(uint16_t) * pair_seg1.size(), cudaMemcpyHostToDevice));
+  if (eng == 2) {
+    put(L.off_task_a, task_a.data(), 4 * task_a.size());
+    put(L.off_task_b, task_b.data(), 4 * task_b.size());
+    put(L.off_hhp_cm, hhp_cm.data(), 4 * hhp_cm.size());
+    put(L.off_lhj, lhj.data(), 4 * lhj.size());
+    put(L.off_lhq, lhq.data(), 2 * lhq.size());
+  } else {
+    put(L.off_item_a, item_a.data(), 2 * item_a.size());
+    put(L.off_item_b, item_b.data(), 2 * item_b.size());
+    { auto t = narrow8(k_of_q); put(L.off_k_of_q, t.data(), t.size()); }
+    { auto t = narrow16(hi_goff); put(L.off_hi_goff, t.data(), 2 * t.size()); }
+    { auto t = narrow16(hi_sbase); put(L.off_hi_sbase, t.data(), 2 * t.size()); }
+    { auto t = narrow8(hi_k); put(L.off_hi_k, t.data(), t.size()); }
+    put(L.off_hh_ptr, hh_ptr.data(), 4 * hh_ptr.size());
+    put(L.off_lh_hi, lh_hi.data(), 2 * lh_hi.size());
+    put(L.off_lh_lo, lh_lo.data(), lh_lo.size());
+  }
+  T.ok = true;
+  return CMPY_OK;
+}
+
+// Builds the class-major tables for the dn species and uploads them.  ok=false (no error) when
+// the sector is outside what the kernel supports.
+static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
+                            const int* s1, const int* s2, int sign_width, const double* eps,
+                            i64 smem_optin, int eng = 0) {
+  T.ok = false;
+  ClsHost H;
+  int rc = build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, smem_optin, eng);
+  if (rc || !H.ok) return rc;
+  T.lay = H.lay; T.e_dn_const = H.e_dn_const; T.smem = H.smem;
+  CU_CHECK(cudaMalloc(&T.d_blob, H.blob.size()));
+  CU_CHECK(cudaMemcpy(T.d_blob, H.blob.data(), H.blob.size(), cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMalloc(&T.d_pair_seg, sizeof(uint16_t) * std::max<size_t>(H.pair_seg.size(), 1)));
+  CU_CHECK(cudaMemcpy(T.d_pair_seg, H.pair_seg.data(), sizeof(uint16_t) * H.pair_seg.size(), cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMalloc(&T.d_pair_seg1, sizeof(uint16_t) * H.pair_seg1.size()));
+  CU_CHECK(cudaMemcpy(T.d_pair_seg1, H.pair_seg1.data(), sizeof(uint16_t) * H.pair_seg1.size(), cudaMemcpyHostToDevice));
   T.ok = true;
   return CMPY_OK;
 }
@@ -744,7 +1099,7 @@ static int upload_vec(T*& dptr, const std::vector<T>& v) {
 // take (odd length ...); without it such a sector makes the whole table set unavailable.
 static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                              const int* s1, const int* s2, int sign_width, const double* eps,
-                             i64 smem_optin, std::vector<int>* skipped = nullptr) {
+                             i64 smem_optin, std::vector<int>* skipped = nullptr, int eng = 0) {
   T.release();
   const u64* B = host_binom();
   const int R = LONG_RBITS, tb = num_sites - R;
@@ -781,7 +1136,7 @@ static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn,
     S.pt = pt;
     S.row_len = (int)B[R * BINOM_N + nr];
     int rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
-                              eps, smem_optin);
+                              eps, smem_optin, eng);
     if (rc) { S.release(); return rc; }
     if (!S.cls.ok) {
       S.release();

@@ -42,12 +42,15 @@ struct HubbardOp : cmpy_op_s {
   bool seg_wide = false;     // 1024-thread CTAs (one CTA per SM, long rows)
   LongTables lng;            // rows of more than 16 sites: sub-row launches of the class-major kernel
   ClsTables cls;             // class-major two-phase kernel (uniform models, long rows)
+  ClsTables cls2;            // the same sector with the engine-2 table set (chunked tasks)
+  LongTables lng2;           // long rows, engine 2
+  int cls_engine = 0;        // engine the default (variant 0) class-major launches use: 0 or 2
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
 
   ~HubbardOp() override {
-    up.release(); dn.release(); seg.release(); cls.release(); lng.release();
+    up.release(); dn.release(); seg.release(); cls.release(); lng.release(); cls2.release(); lng2.release();
     cudaFree(d_hop); cudaFree(d_u);
   }
 
@@ -113,9 +116,17 @@ struct HubbardOp : cmpy_op_s {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
     if (use_variant == 8 && !(lng.ok && UNI && aligned16 && !p.with_up && !LZ && (p.num_dn % 2 == 0)))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant not available for this call");
+    if (use_variant == 10 && !(lng2.ok && UNI && aligned16 && !p.with_up && !LZ && (p.num_dn % 2 == 0)))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant (engine 2) not available for this call");
+    if (use_variant == 9 && !(cls2.ok && UNI && aligned16))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant (engine 2) not available for this call");
+    if (use_variant == 10) return launch_long(p, st, lng2, 2);
     if (use_variant == 8 || (use_variant == 0 && lng.ok && UNI && aligned16 && !p.with_up && !LZ &&
-                             (p.num_dn % 2 == 0)))
-      return launch_long(p, st);
+                             (p.num_dn % 2 == 0))) {
+      if (use_variant == 0 && cls_engine == 2 && lng2.ok) return launch_long(p, st, lng2, 2);
+      return launch_long(p, st, lng, 0);
+    }
+    if (use_variant == 9) return launch_cls<LZ>(p, st, 2);
     if (use_variant >= 5 && use_variant <= 7 && !aligned16)
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant needs 16-byte aligned vectors");
     // default: the segment kernel for the full H.v (its up-hop gathers overlap the shared-memory
@@ -123,9 +134,10 @@ struct HubbardOp : cmpy_op_s {
     // hops (sharded operator: 2.1 vs 2.97 ms)
     if ((use_variant >= 5 && use_variant <= 7) ||
         (use_variant == 0 && cls.ok && cls_default && UNI && aligned16 && !p.with_up)) {
+      if (use_variant == 0 && cls_engine == 2 && cls2.ok) return launch_cls<LZ>(p, st, 2);
       const int saved = cls_shape;
       if (use_variant >= 5) cls_shape = use_variant - 5;
-      int rc = launch_cls<LZ>(p, st);
+      int rc = launch_cls<LZ>(p, st, 0);
       cls_shape = saved;
       return rc;
     }
@@ -194,12 +206,19 @@ struct HubbardOp : cmpy_op_s {
   }
 
   template <bool LZ>
-  int launch_cls(HubParams& p, cudaStream_t st) {
+  int launch_cls(HubParams& p, cudaStream_t st, int eng) {
+    const ClsTables& T = eng == 2 ? cls2 : cls;
     ClsParams cp;
-    cp.hp = p; cp.lay = cls.lay; cp.blob = cls.d_blob; cp.pair_seg = cls.d_pair_seg; cp.e_dn_const = cls.e_dn_const;
+    cp.hp = p; cp.lay = T.lay; cp.blob = T.d_blob; cp.pair_seg = T.d_pair_seg; cp.e_dn_const = T.e_dn_const;
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
+    if (eng == 2) {  // engine 2: chunked tasks (1024-thread shapes only)
+      if (!p.with_up) hub_cls_kernel<LZ, 1024, 0, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
+      else hub_cls_kernel<LZ, 1024, 8, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
+      KERNEL_CHECK();
+      return CMPY_OK;
+    }
     // (896 / 768 threads measured 2.36 / 2.43 ms vs 2.12 ms for 1024 on the 4x4 sector: issue-bound)
     if (!p.with_up) hub_cls_kernel<LZ, 1024, 0><<<(int)g, 1024, cls.smem, st>>>(cp);
     else if (cls_shape == 1) hub_cls_kernel<LZ, 512, 16><<<(int)g, 512, cls.smem, st>>>(cp);
@@ -210,19 +229,20 @@ struct HubbardOp : cmpy_op_s {
   }
 
   // dn-only pass over rows longer than shared memory: one launch per popcount of the top bits
-  int launch_long(HubParams& p, cudaStream_t st) {
-    for (auto& S : lng.sets) {
+  int launch_long(HubParams& p, cudaStream_t st, LongTables& lt, int eng) {
+    for (auto& S : lt.sets) {
       ClsParams cp;
       cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
-      cp.e_dn_const = lng.e_dn_const;
-      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lng.nsb; cp.lg.shift = S.shift;
+      cp.e_dn_const = lt.e_dn_const;
+      cp.lg.ntop = S.ntop; cp.lg.row_len = S.row_len; cp.lg.nsb = lt.nsb; cp.lg.shift = S.shift;
       cp.lg.top_val = S.d_top_val; cp.lg.sub_off = S.d_sub_off; cp.lg.tb_ptr = S.d_tb_ptr;
       cp.lg.tb_ent = S.d_tb_ent; cp.lg.sb_src = S.d_sb_src; cp.lg.sb_map = S.d_sb_map;
       i64 g = sm_count;
       if (grid_limit > 0 && g > grid_limit) g = grid_limit;
       const i64 items = p.nrows * S.ntop;
       if (g > items) g = items;
-      hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      if (eng == 2) hub_cls_kernel<false, 1024, 8, true, false, 2><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      else hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
       KERNEL_CHECK();
     }
     return CMPY_OK;
@@ -238,6 +258,18 @@ struct HubbardOp : cmpy_op_s {
       int nb = 0;
       CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<false, 1024, 8, true>, 1024, S.cls.smem));
       if (nb < 1) { lng.release(); return CMPY_OK; }
+    }
+    // engine 2 (chunked tasks): same sub-row decomposition, its own table set
+    rc = build_long_tables(lng2, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, nullptr, 2);
+    if (rc) return rc;
+    if (lng2.ok) {
+      rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, true, false, 2>, smem_optin);
+      if (rc) return rc;
+      for (auto& S : lng2.sets) {
+        int nb = 0;
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<false, 1024, 8, true, false, 2>, 1024, S.cls.smem));
+        if (nb < 1) { lng2.release(); break; }
+      }
     }
     return CMPY_OK;
   }
@@ -260,6 +292,18 @@ struct HubbardOp : cmpy_op_s {
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8>, 1024, cls.smem));
     if (nb < 1) { cls.ok = false; return CMPY_OK; }
     cls_default = dn.num >= 2048;  // long rows: one CTA per SM anyway
+    // engine 2 (chunked tasks): its own table set, 1024-thread shapes
+    rc = build_cls_tables(cls2, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, 2);
+    if (rc) return rc;
+    if (cls2.ok) {
+      rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 1024, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 0, false, false, 2>, smem_optin);
+      if (rc) return rc;
+      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8, false, false, 2>, 1024, cls2.smem));
+      if (nb < 1) cls2.release();
+    }
     return CMPY_OK;
   }
 

@@ -1,0 +1,148 @@
+// cls_emu.cu -- TEST INFRASTRUCTURE (not part of the product): runs the shared-memory phases of
+// the class-major H.v kernel (cmpy_b200/csrc/hubbard_cls.cuh) lane by lane on the CPU.
+//
+// The phase bodies (cls_phase_a/b = engine 0, cls2_phase_a/b = engine 2) are __host__ __device__;
+// inside one phase every (warp, lane) only reads what the previous phase wrote and writes its
+// own slots, so executing the lanes one after the other is exactly what the barrier-separated
+// kernel computes.  Staging and un-staging follow the kernel's column-pair -> slot map
+// (pair_seg + seg_delta).  tests/test_cls_emulation.py compares the result with a direct
+// evaluation of (D + T_dn) x on one row (ref: cmpy/operators.py:305-527).
+//
+// Built by the test itself:  nvcc -O1 -std=c++17 -shared -Xcompiler -fPIC cls_emu.cu
+#include "../../cmpy_b200/csrc/hubbard_cls.cuh"
+#include <cmath>
+
+template <bool SPIN>
+static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<double>& xs,
+                       std::vector<double>& ys, uint32_t ups, double eu, double u0, double hop0,
+                       int nwarps) {
+  const ClsLayout& L = H.lay;
+  const unsigned char* tab = H.blob.data();
+  if (L.eng == 2) {
+    const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
+    const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
+    for (int warp = 0; warp < nwarps; ++warp)   // the task loops of hub_cls_kernel<..., ENG = 2>
+      for (int pc = warp; pc < CLS2_PIECES; pc += nwarps)
+        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
+          for (int lane = 0; lane < 32; ++lane)
+            cls2_task_a<SPIN>(L, sd, tab, xs.data(), ys.data(), task_a[it], ups, eu, u0, hop0, lane);
+    for (int warp = 0; warp < nwarps; ++warp)
+      for (int pc = warp; pc < CLS2_PIECES; pc += nwarps)
+        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it)
+          for (int lane = 0; lane < 32; ++lane)
+            cls2_task_b(L, tab, xs.data(), ys.data(), task_b[it], hop0, lane);
+    return;
+  }
+  // engine 0: the item headers of hub_cls_kernel, verbatim
+  const uint16_t* item_a = reinterpret_cast<const uint16_t*>(tab + L.off_item_a);
+  const uint16_t* item_b = reinterpret_cast<const uint16_t*>(tab + L.off_item_b);
+  const uint8_t* k_of_q = tab + L.off_k_of_q;
+  const uint16_t* dl_of_q = reinterpret_cast<const uint16_t*>(tab + L.off_dl_of_q);
+  const uint32_t* ll_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_ll_ptr);
+  const uint8_t* ll_ent = tab + L.off_ll_ent;
+  const uint16_t* dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list);
+  const uint16_t* hi_sbase = reinterpret_cast<const uint16_t*>(tab + L.off_hi_sbase);
+  const uint8_t* hi_k = tab + L.off_hi_k;
+  const uint32_t* hh_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ptr);
+  const uint16_t* hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
+  const uint16_t* lh_hi = reinterpret_cast<const uint16_t*>(tab + L.off_lh_hi);
+  const uint8_t* lh_lo = tab + L.off_lh_lo;
+  for (int it = 0; it < L.na; ++it)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int q = item_a[it];
+      const int k = k_of_q[q];
+      const uint32_t pp = ll_ptr[q];
+      const uint32_t dlbits = dl_of_q[q];
+      const int hk = L.H[k], r = q - L.qoff[k];
+      if (hk <= 32) cls_phase_a<1, SPIN>(L, sd, xs.data(), ys.data(), ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+      else if (hk <= 64) cls_phase_a<2, SPIN>(L, sd, xs.data(), ys.data(), ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+      else cls_phase_a<3, SPIN>(L, sd, xs.data(), ys.data(), ll_ent, dh_list, pp, k, r, dlbits, ups, eu, u0, hop0, lane);
+    }
+  for (int it = 0; it < L.nb; ++it)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int dh = item_b[it];
+      const int k = hi_k[dh];
+      const uint32_t pp = hh_ptr[dh];
+      const int sb = hi_sbase[dh], sk = L.S[k];
+      if (sk <= 32) cls_phase_b<1>(L, xs.data(), ys.data(), hh_ent, lh_hi, lh_lo, pp, k, dh, sb, hop0, lane);
+      else if (sk <= 64) cls_phase_b<2>(L, xs.data(), ys.data(), hh_ent, lh_hi, lh_lo, pp, k, dh, sb, hop0, lane);
+      else cls_phase_b<3>(L, xs.data(), ys.data(), hh_ent, lh_hi, lh_lo, pp, k, dh, sb, hop0, lane);
+    }
+}
+
+// One row of y = (D + T_dn) x through the emulated phases.
+//   spin = 0: Hubbard flavour, diag = eu + u0 * popc(ups & dn)
+//   spin = 1: XXZ flavour, diag = sd_e0 + sd_escale * #antiparallel bonds (bonds grouped by site
+//             distance as in heisenberg.cuh), hops without sign (pass sign_width = 0)
+// returns 0 ok, 1 sector not supported by the table builder, 2 bad argument, 3 a slot was not written
+extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, const int* s2,
+                           int sign_width, double eps0, double u0, double hop0, unsigned ups, double eu,
+                           int eng, int spin, double sd_e0, double sd_escale, int nwarps,
+                           const double* x_row, double* y_row, int* info) {
+  const u64* B = host_binom();
+  if (num_sites < 2 || num_sites > 16 || n_dn < 0 || n_dn > num_sites || nwarps < 1) return 2;
+  const i64 num_dn = (i64)B[num_sites * BINOM_N + n_dn];
+  ClsHost H;
+  const double eps[1] = {eps0};
+  if (build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448, eng)) return 2;
+  if (!H.ok) return 1;
+  const ClsLayout& L = H.lay;
+  SpinDiag sd;
+  memset(&sd, 0, sizeof(sd));
+  if (spin) {
+    for (int k = 0; k < nbonds; ++k) {
+      const int delta = s2[k] - s1[k];
+      int i = 0;
+      for (; i < sd.ndelta; ++i) if (sd.delta[i] == delta) break;
+      if (i == sd.ndelta) {
+        if (sd.ndelta == 4) return 1;
+        sd.delta[sd.ndelta++] = delta;
+      }
+      sd.dmask[i] |= 1u << s1[k];
+    }
+    sd.e0 = sd_e0; sd.escale = sd_escale;
+  }
+  const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
+  std::vector<double> xs(xs_total, 0.0), ys(L.xs_elems, std::nan(""));
+  const int16_t* seg_delta = reinterpret_cast<const int16_t*>(H.blob.data() + L.off_seg_delta);
+  const int npairs = (int)(num_dn / 2);
+  std::vector<int> slot(num_dn, -1);
+  for (int pi = 0; pi < npairs; ++pi) {   // the staging loop of hub_cls_kernel (shift = 0)
+    const uint32_t ps = H.pair_seg[pi];
+    const int si = (int)(ps & 0x7fffu), d = 2 * pi;
+    slot[d] = d + seg_delta[si];
+    slot[d + 1] = d + 1 + seg_delta[si + (int)(ps >> 15)];
+  }
+  for (i64 d = 0; d < num_dn; ++d) {
+    if (slot[d] < 0 || slot[d] >= L.xs_elems) return 3;
+    xs[slot[d]] = x_row[d];
+  }
+  if (spin) run_phases<true>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
+  else run_phases<false>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
+  for (i64 d = 0; d < num_dn; ++d) {
+    y_row[d] = ys[slot[d]];
+    if (std::isnan(y_row[d])) return 3;
+  }
+  if (info) {
+    info[0] = L.bytes; info[1] = (int)H.smem; info[2] = L.eng == 2 ? L.nta : L.na;
+    info[3] = L.eng == 2 ? L.ntb : L.nb; info[4] = L.nlh; info[5] = L.xs_elems;
+    if (L.eng == 2) {  // balance of the phase-A / phase-B pieces in (32-lane block x column) units
+      const uint32_t* tk[2] = {reinterpret_cast<const uint32_t*>(H.blob.data() + L.off_task_a),
+                               reinterpret_cast<const uint32_t*>(H.blob.data() + L.off_task_b)};
+      for (int ph = 0; ph < 2; ++ph) {
+        const uint16_t* ptr = ph ? L.ptr_b : L.ptr_a;
+        int mx = 0, tot = 0;
+        for (int pc = 0; pc < CLS2_PIECES; ++pc) {
+          int w = 0;
+          for (int it = ptr[pc]; it < ptr[pc + 1]; ++it) {
+            const int k = tk[ph][it] & 0xff, n = tk[ph][it] >> 16;
+            w += (((ph ? L.S[k] : L.H[k]) + 31) / 32) * n;
+          }
+          mx = w > mx ? w : mx; tot += w;
+        }
+        info[6 + 2 * ph] = mx; info[7 + 2 * ph] = tot;
+      }
+    }
+  }
+  return 0;
+}
