@@ -147,6 +147,26 @@ CLS_HD double cls_flip(double v, uint32_t signmask) {
 #endif
 }
 CLS_HD int cls_min(int a, int b) { return a < b ? a : b; }
+// Engine 2 addresses shared memory through explicit byte addresses (32-bit shared-space addresses
+// on the device, so that "per-lane base + warp-uniform offset" is one LEA/IADD per access instead
+// of a re-derivation from the buffer base; plain pointers on the host).
+#ifdef __CUDA_ARCH__
+typedef uint32_t cls_addr;
+__device__ __forceinline__ cls_addr cls_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double cls_ld(cls_addr a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void cls_st(cls_addr a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+#else
+typedef uintptr_t cls_addr;
+inline cls_addr cls_base(const void* p) { return (uintptr_t)p; }
+inline double cls_ld(cls_addr a) { return *reinterpret_cast<const double*>(a); }
+inline void cls_st(cls_addr a, double v) { *reinterpret_cast<double*>(a) = v; }
+#endif
 
 // ---- phase A body: one (k, r) pair, T blocks of 32 dh-segments (lanes along jj) ----
 template <int T, bool SPIN>
@@ -279,16 +299,19 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
   const uint16_t* __restrict__ dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list) + L.hoff[k];
   const uint32_t* __restrict__ lhj = reinterpret_cast<const uint32_t*>(tab + L.off_lhj) + L.hoff[k];
   const uint16_t* __restrict__ lhq = reinterpret_cast<const uint16_t*>(tab + L.off_lhq) + L.qoff[k];
-  int o[T];             // element offset of (jj, r = 0); lanes past the class recompute its last segment
+  const cls_addr xs_a = cls_base(xs);
+  const cls_addr y_minus_x = cls_base(ys) - xs_a;   // the two buffers have the same layout
+  // hoisted per-lane state; lanes past the class recompute its last segment and never store
+  cls_addr xa[T];       // address of xs[(jj, r = 0)]
   uint32_t dhs[T];      // dh bits of the lane's segments, already shifted to their place in the string
   uint32_t lh[CLS2_MAX_LH][T];
-  int ph[T];            // popcount of (ups & dh part)
+  double dgh[T];        // eu + u0 * popc(ups & dh part)
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int jj = cls_min(lane + 32 * t, hk - 1);
-    o[t] = xb + jj * pk;
+    xa[t] = xs_a + (cls_addr)(xb + jj * pk) * 8u;
     dhs[t] = (uint32_t)dh_list[jj] << L.m;
-    ph[t] = SPIN ? 0 : cls_popc(ups & dhs[t]);
+    dgh[t] = SPIN ? 0.0 : eu + u0 * (double)cls_popc(ups & dhs[t]);
 #pragma unroll
     for (int b = 0; b < CLS2_MAX_LH; ++b) lh[b][t] = b < nlh ? lhj[b * L.nseg + jj] : 0u;
   }
@@ -305,18 +328,16 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
 #pragma unroll 1
       for (; i < npos; ++i) {
         const uint32_t e = ent2[i];
-        const double* __restrict__ q0 = xs + (e & 0xffu);
-        const double* __restrict__ q1 = xs + (e >> 8);
+        const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
 #pragma unroll
-        for (int t = 0; t < T; ++t) { ap[t] += q0[o[t]]; an[t] -= q1[o[t]]; }
+        for (int t = 0; t < T; ++t) { ap[t] += cls_ld(xa[t] + e0); an[t] -= cls_ld(xa[t] + e1); }
       }
 #pragma unroll 1
       for (; i < ntot; ++i) {
         const uint32_t e = ent2[i];
-        const double* __restrict__ q0 = xs + (e & 0xffu);
-        const double* __restrict__ q1 = xs + (e >> 8);
+        const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
 #pragma unroll
-        for (int t = 0; t < T; ++t) { an[t] += q0[o[t]]; ap[t] -= q1[o[t]]; }
+        for (int t = 0; t < T; ++t) { an[t] += cls_ld(xa[t] + e0); ap[t] -= cls_ld(xa[t] + e1); }
       }
     }
 #pragma unroll
@@ -324,19 +345,20 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
       if (b < nlh) {
         const uint32_t w = lhq[b * L.nq + r];
         if (w & 0x200u) {
-          const double* __restrict__ xq = xs + (w & 0x7fu);
+          const cls_addr xq = xs_a + (cls_addr)(w & 0x7fu) * 8u;
           const int sh = (w & 0x100u) ? 14 : 0;
           const uint32_t sgn = (w & 0x80u) << 24;   // parity of the dl part -> sign bit position
 #pragma unroll
           for (int t = 0; t < T; ++t) {
             const uint32_t e = lh[b][t];
-            ap[t] += cls_flip(xq[(e >> sh) & 0x3fffu], (e ^ sgn) & 0x80000000u);
+            ap[t] += cls_flip(cls_ld(xq + (cls_addr)((e >> sh) & 0x3fffu) * 8u), (e ^ sgn) & 0x80000000u);
           }
         }
       }
     }
     const uint32_t dlbits = dl_of_q[r];
-    const int pl = SPIN ? 0 : cls_popc(ups & dlbits);
+    const double dgl = SPIN ? 0.0 : u0 * (double)cls_popc(ups & dlbits);
+    const cls_addr r8 = (cls_addr)r * 8u;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       if (lane + 32 * t < hk) {
@@ -347,9 +369,9 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
           for (int i = 0; i < sd.ndelta; ++i) cnt += cls_popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
           diag = sd.e0 + sd.escale * (double)cnt;
         } else {
-          diag = eu + u0 * (double)(ph[t] + pl);
+          diag = dgh[t] + dgl;   // = eu + u0 * popc(ups & dn) up to one rounding
         }
-        ys[o[t] + r] = diag * xs[o[t] + r] + hop0 * (ap[t] - an[t]);
+        cls_st(xa[t] + r8 + y_minus_x, diag * cls_ld(xa[t] + r8) + hop0 * (ap[t] - an[t]));
       }
     }
   }
@@ -363,7 +385,8 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
   const int sk = L.S[k], pk = L.P[k];
   const uint32_t* __restrict__ hhp = reinterpret_cast<const uint32_t*>(tab + L.off_hhp_cm) + L.hoff[k];
   const uint16_t* __restrict__ hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
-  const double* __restrict__ xp0 = xs + lane;
+  const cls_addr xl = cls_base(xs) + (cls_addr)lane * 8u;
+  const cls_addr yl = cls_base(ys) + (cls_addr)(L.xbase[k] + lane) * 8u;
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + njj; ++jj) {
     const uint32_t pp = hhp[jj];
@@ -377,23 +400,21 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
 #pragma unroll 1
     for (; i < npos; ++i) {
       const uint32_t e = ent2[i];
-      const double* __restrict__ q0 = xp0 + (e & 0xffffu);
-      const double* __restrict__ q1 = xp0 + (e >> 16);
+      const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
 #pragma unroll
-      for (int t = 0; t < T; ++t) { hp[t] += q0[32 * t]; hn[t] -= q1[32 * t]; }
+      for (int t = 0; t < T; ++t) { hp[t] += cls_ld(q0 + 256u * t); hn[t] -= cls_ld(q1 + 256u * t); }
     }
 #pragma unroll 1
     for (; i < ntot; ++i) {
       const uint32_t e = ent2[i];
-      const double* __restrict__ q0 = xp0 + (e & 0xffffu);
-      const double* __restrict__ q1 = xp0 + (e >> 16);
+      const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
 #pragma unroll
-      for (int t = 0; t < T; ++t) { hn[t] += q0[32 * t]; hp[t] -= q1[32 * t]; }
+      for (int t = 0; t < T; ++t) { hn[t] += cls_ld(q0 + 256u * t); hp[t] -= cls_ld(q1 + 256u * t); }
     }
-    double* __restrict__ yp0 = ys + L.xbase[k] + jj * pk + lane;
+    const cls_addr yp = yl + (cls_addr)(jj * pk) * 8u;
 #pragma unroll
     for (int t = 0; t < T; ++t)
-      if (lane + 32 * t < sk) yp0[32 * t] += hop0 * (hp[t] - hn[t]);
+      if (lane + 32 * t < sk) cls_st(yp + 256u * t, cls_ld(yp + 256u * t) + hop0 * (hp[t] - hn[t]));
   }
 }
 

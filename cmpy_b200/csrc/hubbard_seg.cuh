@@ -233,16 +233,18 @@ __global__ void __launch_bounds__(NT, 1) hub_seg_kernel(SegParams sp) {
             if (k0 + k < cu) { const double c = s_up[k0 + k].coef; a0 += c * g[k].x; a1 += c * g[k].y; }
         }
         double2* yp = reinterpret_cast<double2*>(yr + d);
+        // streaming stores: y is not read again before it has left L2 (microbenchmark: 2.09 vs
+        // 2.18 ms for the gather part with st.cs), the cache stays with the gathered rows of x
         if (LZ) {
           double w0 = s1 * a0, w1 = s1 * a1;
           if (has_prev) { const double2 yo = *yp; w0 -= s2 * yo.x; w1 -= s2 * yo.y; }
-          *yp = make_double2(w0, w1);
+          __stcs(yp, make_double2(w0, w1));
           dot += (s1 * xi.x) * w0 + (s1 * xi.y) * w1;
         } else if (p.accumulate) {
           const double2 yo = *yp;
-          *yp = make_double2(yo.x + a0, yo.y + a1);
+          __stcs(yp, make_double2(yo.x + a0, yo.y + a1));
         } else {
-          *yp = make_double2(a0, a1);
+          __stcs(yp, make_double2(a0, a1));
         }
       }
     } else {
