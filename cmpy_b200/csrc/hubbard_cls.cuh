@@ -28,10 +28,12 @@
 #pragma once
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 #include "hubbard_seg.cuh"
 
 #define CLS_MAX_CLS 12
-#define CLS2_PIECES 32   // engine 2: work pieces per phase (= warps of a 1024-thread CTA)
+#define CLS2_MAX_PIECES 128   // engine 2: upper bound on the work pieces per phase
+#define CLS2_DEF_PIECES 64    // default: two pieces per warp of a 1024-thread CTA
 #define CLS_ZREG 96  // zero region appended to xs (target of HH list padding)
 
 struct ClsLayout {
@@ -68,7 +70,8 @@ struct ClsLayout {
                      //     hop is not allowed for that value; bit 31 = parity of the dh part
   int off_lhq;       // u16 [nlh][nq]   per (k, r): r' | parity of the dl part << 7 | dl bit << 8 |
                      //     source class exists << 9
-  uint16_t ptr_a[CLS2_PIECES + 1], ptr_b[CLS2_PIECES + 1];  // tasks of piece i: [ptr[i], ptr[i+1])
+  int npieces;       // work pieces per phase
+  uint16_t ptr_a[CLS2_MAX_PIECES + 1], ptr_b[CLS2_MAX_PIECES + 1];  // tasks of piece i: [ptr[i], ptr[i+1])
   int bytes;
 };
 
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
     // ---- phase A: lanes along jj, LL hops + diagonal -> ys ----
     if (ENG == 2) {
       const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
-      for (int pc = warp; pc < CLS2_PIECES; pc += NW)
+      for (int pc = warp; pc < L.npieces; pc += NW)
         for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
           cls2_task_a<SPIN>(L, cp.sd, tab, xs, ys, task_a[it], ups, eu, u0, hop0, lane);
     } else
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
     // ---- phase B: lanes along r, HH + LH hops accumulated into ys ----
     if (ENG == 2) {
       const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
-      for (int pc = warp; pc < CLS2_PIECES; pc += NW)
+      for (int pc = warp; pc < L.npieces; pc += NW)
         for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it) cls2_task_b(L, tab, xs, ys, task_b[it], hop0, lane);
     } else
     for (int it = warp; it < L.nb; it += NW) {
@@ -905,18 +908,23 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
   if (eng == 2) {
     if (L.nlh > CLS2_MAX_LH || m > 8 || hb > 8) return CMPY_OK;  // task fields are 8 bits wide
     // The (k, r) columns of phase A / (k, jj) segments of phase B, in class-major order, are cut
-    // into CLS2_PIECES contiguous pieces of about equal estimated cost (32-lane blocks x list
-    // entries); a piece that spans a class boundary becomes several tasks.  Warp w of the CTA
-    // takes the pieces w, w + NW, ... -- with 32 warps exactly one piece each, so the per-lane
-    // state is set up once or twice per row and the warps finish together.
-    auto partition = [&](std::vector<uint32_t>& out, std::vector<uint16_t>& ptr, const int* lanes_dim,
-                         const int* loop_dim, auto&& cost) {
+    // into npieces contiguous pieces of about equal estimated cost; a piece that spans a class
+    // boundary becomes several tasks.  Warp w of the CTA takes the pieces w, w + NW, ...
+    // The cost model counts issued instructions of the compiled loops (SASS of sm_100a):
+    //   phase A, per column: 25 + (pairs + LH bonds) * (9 + 6 T) + 10 T     (T = 32-lane blocks)
+    //   phase B, per segment: 12 + pairs * (9 + 4 T) + 6 T
+    int npieces = CLS2_DEF_PIECES;
+    if (const char* e = getenv("CMPY_CLS_PIECES")) npieces = atoi(e);
+    if (npieces < 1) npieces = 1;
+    if (npieces > CLS2_MAX_PIECES) npieces = CLS2_MAX_PIECES;
+    L.npieces = npieces;
+    auto partition = [&](std::vector<uint32_t>& out, uint16_t* ptr, const int* loop_dim, auto&& cost) {
       double total = 0.0;
       for (int k = 0; k <= m; ++k)
         if (L.H[k] > 0)
-          for (int c = 0; c < loop_dim[k]; ++c) total += ((lanes_dim[k] + 31) / 32) * cost(k, c);
+          for (int c = 0; c < loop_dim[k]; ++c) total += cost(k, c);
       out.clear();
-      ptr.assign(CLS2_PIECES + 1, 0);
+      for (int i = 0; i <= CLS2_MAX_PIECES; ++i) ptr[i] = 0;
       double acc = 0.0;
       int piece = 0, cur_k = -1, c0 = 0, n = 0;
       auto flush = [&]() {
@@ -926,10 +934,11 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
       for (int k = 0; k <= m; ++k) {
         if (L.H[k] <= 0) continue;
         for (int c = 0; c < loop_dim[k]; ++c) {
-          const double w = ((lanes_dim[k] + 31) / 32) * cost(k, c);
+          const double w = cost(k, c);
           // close the piece when its share of the total is used up (never leave a piece empty
-          // while work remains, never open more than CLS2_PIECES pieces)
-          if (piece + 1 < CLS2_PIECES && acc + 0.5 * w > total * (piece + 1) / CLS2_PIECES && (n > 0 || (int)out.size() > ptr[piece])) {
+          // while work remains, never open more than npieces pieces)
+          if (piece + 1 < npieces && acc + 0.5 * w > total * (piece + 1) / npieces &&
+              (n > 0 || (int)out.size() > ptr[piece])) {
             flush();
             ptr[++piece] = (uint16_t)out.size();
           }
@@ -940,22 +949,22 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
         }
       }
       flush();
-      while (piece < CLS2_PIECES) ptr[++piece] = (uint16_t)out.size();
+      while (piece < CLS2_MAX_PIECES) ptr[++piece] = (uint16_t)out.size();
     };
-    std::vector<uint16_t> ptr_a, ptr_b;
     auto cost_a = [&](int k, int r) {
+      const int T = (L.H[k] + 31) / 32;
       const uint32_t pp = ll_ptr[L.qoff[k] + r];
-      return 2.0 * (double)(pp >> 24) + (double)L.nlh + 2.0;
+      return 25.0 + (double)((int)(pp >> 24) + L.nlh) * (9.0 + 6.0 * T) + 10.0 * T;
     };
     auto cost_b = [&](int k, int jj) {
+      const int T = (L.S[k] + 31) / 32;
       const uint32_t pp = hh_ptr[dh_list[L.hoff[k] + jj]];
-      return 2.0 * (double)(pp >> 24) + 1.0;
+      return 12.0 + (double)(pp >> 24) * (9.0 + 4.0 * T) + 6.0 * T;
     };
-    partition(task_a, ptr_a, L.H, L.S, cost_a);   // lanes along jj (H_k), loop over r (S_k)
-    partition(task_b, ptr_b, L.S, L.H, cost_b);   // lanes along r (S_k), loop over jj (H_k)
+    partition(task_a, L.ptr_a, L.S, cost_a);   // lanes along jj (H_k), loop over r (S_k)
+    partition(task_b, L.ptr_b, L.H, cost_b);   // lanes along r (S_k), loop over jj (H_k)
     L.nta = (int)task_a.size();
     L.ntb = (int)task_b.size();
-    for (int i = 0; i <= CLS2_PIECES; ++i) { L.ptr_a[i] = ptr_a[i]; L.ptr_b[i] = ptr_b[i]; }
     hhp_cm.assign(std::max(nseg, 1), 0);
     for (int sgi = 0; sgi < nseg; ++sgi) hhp_cm[sgi] = hh_ptr[dh_list[sgi]];
     lhj.assign((size_t)std::max(1, L.nlh) * std::max(nseg, 1), 0);

@@ -22,12 +22,12 @@ static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<d
     const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
     const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
     for (int warp = 0; warp < nwarps; ++warp)   // the task loops of hub_cls_kernel<..., ENG = 2>
-      for (int pc = warp; pc < CLS2_PIECES; pc += nwarps)
+      for (int pc = warp; pc < L.npieces; pc += nwarps)
         for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
           for (int lane = 0; lane < 32; ++lane)
             cls2_task_a<SPIN>(L, sd, tab, xs.data(), ys.data(), task_a[it], ups, eu, u0, hop0, lane);
     for (int warp = 0; warp < nwarps; ++warp)
-      for (int pc = warp; pc < CLS2_PIECES; pc += nwarps)
+      for (int pc = warp; pc < L.npieces; pc += nwarps)
         for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it)
           for (int lane = 0; lane < 32; ++lane)
             cls2_task_b(L, tab, xs.data(), ys.data(), task_b[it], hop0, lane);
@@ -132,7 +132,7 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
       for (int ph = 0; ph < 2; ++ph) {
         const uint16_t* ptr = ph ? L.ptr_b : L.ptr_a;
         int mx = 0, tot = 0;
-        for (int pc = 0; pc < CLS2_PIECES; ++pc) {
+        for (int pc = 0; pc < L.npieces; ++pc) {
           int w = 0;
           for (int it = ptr[pc]; it < ptr[pc + 1]; ++it) {
             const int k = tk[ph][it] & 0xff, n = tk[ph][it] >> 16;
@@ -142,6 +142,7 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
         }
         info[6 + 2 * ph] = mx; info[7 + 2 * ph] = tot;
       }
+      info[10] = L.npieces;
     }
   }
   return 0;

@@ -149,9 +149,11 @@ def test_engines_agree_and_use_fewer_tasks(emu, eng):
     assert rc == 0
     assert info[1] + 2560 <= 232448          # dynamic + static shared memory of one CTA
     if eng == 2:
-        assert info[2] <= 48 and info[3] <= 48   # 32 pieces (+ class boundaries) instead of 256 items
-        # pieces are balanced: the heaviest one is within 45 % of the mean in block x column units (the split balances estimated cost, not columns)
-        assert info[6] * 32 <= 1.45 * info[7] and info[8] * 32 <= 1.45 * info[9], info
+        npc = int(info[10])
+        assert info[2] <= npc + 16 and info[3] <= npc + 16   # pieces (+ class boundaries) instead of 256 items
+        # no piece is far above the mean in block x column units (the split balances the estimated
+        # instruction count, in which a 3-block column costs less than three 1-block columns)
+        assert info[6] * npc <= 2.0 * info[7] and info[8] * npc <= 2.0 * info[9], info
     ref = direct_row(L, n, square(4, 4), L, 4.0, 1.0, 0b1010110010100110, -16.0, x)
     assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
 

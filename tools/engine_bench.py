@@ -13,6 +13,7 @@ import torch  # noqa: E402
 from cmpy_b200.models import HubbardModel  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+mode = sys.argv[2] if len(sys.argv) > 2 else "bench"   # "ncu": one launch per variant, for a profiler run
 out_path = os.path.join(ROOT, "gpurun_out", "engine_bench.jsonl")
 os.makedirs(os.path.dirname(out_path), exist_ok=True)
 out_f = open(out_path, "a")
@@ -89,8 +90,27 @@ def run(name, L, nb, nu, nd, full_variants, slab_variants):
     torch.cuda.empty_cache()
 
 
+def ncu_launches():
+    """One dn-only launch of engine 0 (variant 5) and engine 2 (variant 9) on config C4."""
+    h = HubbardModel(16, square(4, 4), inter=4.0, mu=2.0, hop=1.0).hamilton_operator(8, 8)
+    x = torch.randn(h.shape[0], dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    for v in (5, 9):
+        h.set_variant(v)
+        h.apply_rows(x, 0, len(h.up_states), out=y)
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
+    if mode == "ncu":
+        ncu_launches()
+        sys.exit(0)
+    if mode == "pieces":   # engine 2 with different numbers of work pieces per phase
+        for npc in (32, 48, 64, 96, 128):
+            os.environ["CMPY_CLS_PIECES"] = str(npc)
+            run(f"c4_square4x4_pieces{npc}", 16, square(4, 4), 8, 8, [9], [5, 9])
+        sys.exit(0)
     # BASELINE config C4 and the 16-site chain: 0 = default (segment kernel), 5 = class-major engine 0,
     # 9 = class-major engine 2
     run("c4_square4x4", 16, square(4, 4), 8, 8, [0, 5, 9], [5, 9])
