@@ -153,6 +153,7 @@ CLS_HD int cls_min(int a, int b) { return a < b ? a : b; }
 // Engine 2 addresses shared memory through explicit byte addresses (32-bit shared-space addresses
 // on the device, so that "per-lane base + warp-uniform offset" is one LEA/IADD per access instead
 // of a re-derivation from the buffer base; plain pointers on the host).
+static std::vector<uintptr_t>* g_cls_trace = nullptr;   // host only (tests/emu): addresses of one lane's loads, in order
 #ifdef __CUDA_ARCH__
 typedef uint32_t cls_addr;
 __device__ __forceinline__ cls_addr cls_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,13 +162,18 @@ __device__ __forceinline__ double cls_ld(cls_addr a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ double cls_ld_y(cls_addr a) { return cls_ld(a); }
 __device__ __forceinline__ void cls_st(cls_addr a, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 #else
 typedef uintptr_t cls_addr;
 inline cls_addr cls_base(const void* p) { return (uintptr_t)p; }
-inline double cls_ld(cls_addr a) { return *reinterpret_cast<const double*>(a); }
+inline double cls_ld(cls_addr a) {
+  if (g_cls_trace) g_cls_trace->push_back(a);
+  return *reinterpret_cast<const double*>(a);
+}
+inline double cls_ld_y(cls_addr a) { return *reinterpret_cast<const double*>(a); }   // predicated load: not traced
 inline void cls_st(cls_addr a, double v) { *reinterpret_cast<double*>(a) = v; }
 #endif
 
@@ -362,6 +368,9 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
     const uint32_t dlbits = dl_of_q[r];
     const double dgl = SPIN ? 0.0 : u0 * (double)cls_popc(ups & dlbits);
     const cls_addr r8 = (cls_addr)r * 8u;
+    double xv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) xv[t] = cls_ld(xa[t] + r8);   // (clamped lanes re-read the last segment)
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       if (lane + 32 * t < hk) {
@@ -374,7 +383,7 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
         } else {
           diag = dgh[t] + dgl;   // = eu + u0 * popc(ups & dn) up to one rounding
         }
-        cls_st(xa[t] + r8 + y_minus_x, diag * cls_ld(xa[t] + r8) + hop0 * (ap[t] - an[t]));
+        cls_st(xa[t] + r8 + y_minus_x, diag * xv[t] + hop0 * (ap[t] - an[t]));
       }
     }
   }
@@ -417,7 +426,7 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
     const cls_addr yp = yl + (cls_addr)(jj * pk) * 8u;
 #pragma unroll
     for (int t = 0; t < T; ++t)
-      if (lane + 32 * t < sk) cls_st(yp + 256u * t, cls_ld(yp + 256u * t) + hop0 * (hp[t] - hn[t]));
+      if (lane + 32 * t < sk) cls_st(yp + 256u * t, cls_ld_y(yp + 256u * t) + hop0 * (hp[t] - hn[t]));
   }
 }
 

@@ -12,6 +12,8 @@
 #include "../../cmpy_b200/csrc/hubbard_cls.cuh"
 #include <cmath>
 
+static long long g_wave_a[3], g_wave_b[3];   // wavefronts, ideal wavefronts, divergent tasks
+
 template <bool SPIN>
 static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<double>& xs,
                        std::vector<double>& ys, uint32_t ups, double eu, double u0, double hop0,
@@ -21,16 +23,49 @@ static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<d
   if (L.eng == 2) {
     const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
     const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
+    // Shared-memory wavefronts of the 8-byte loads of one warp-level task: the lanes of a warp run
+    // the same instruction sequence, so load i of every lane is one LDS.64; each half warp costs
+    // as many wavefronts as the most loaded 8-byte bank has distinct addresses.
+    std::vector<uintptr_t> tr[32];
+    auto account = [&](long long* acc) {
+      const size_t n = tr[0].size();
+      for (int l = 1; l < 32; ++l) if (tr[l].size() != n) { acc[2] += 1; return; }   // divergent: not counted
+      for (size_t i = 0; i < n; ++i)
+        for (int half = 0; half < 2; ++half) {
+          uintptr_t seen[16][16]; int cnt[16] = {0};
+          int worst = 0;
+          for (int l = 16 * half; l < 16 * half + 16; ++l) {
+            const uintptr_t a = tr[l][i];
+            const int bank = (int)((a >> 3) & 15);
+            bool dup = false;
+            for (int j = 0; j < cnt[bank]; ++j) dup |= seen[bank][j] == a;
+            if (!dup) seen[bank][cnt[bank]++] = a;
+            worst = cnt[bank] > worst ? cnt[bank] : worst;
+          }
+          acc[0] += worst;   // wavefronts
+          acc[1] += 1;       // ideal: one per half warp
+        }
+    };
     for (int warp = 0; warp < nwarps; ++warp)   // the task loops of hub_cls_kernel<..., ENG = 2>
       for (int pc = warp; pc < L.npieces; pc += nwarps)
-        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
-          for (int lane = 0; lane < 32; ++lane)
+        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it) {
+          for (int lane = 0; lane < 32; ++lane) {
+            tr[lane].clear(); g_cls_trace = &tr[lane];
             cls2_task_a<SPIN>(L, sd, tab, xs.data(), ys.data(), task_a[it], ups, eu, u0, hop0, lane);
+          }
+          g_cls_trace = nullptr;
+          account(g_wave_a);
+        }
     for (int warp = 0; warp < nwarps; ++warp)
       for (int pc = warp; pc < L.npieces; pc += nwarps)
-        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it)
-          for (int lane = 0; lane < 32; ++lane)
+        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it) {
+          for (int lane = 0; lane < 32; ++lane) {
+            tr[lane].clear(); g_cls_trace = &tr[lane];
             cls2_task_b(L, tab, xs.data(), ys.data(), task_b[it], hop0, lane);
+          }
+          g_cls_trace = nullptr;
+          account(g_wave_b);
+        }
     return;
   }
   // engine 0: the item headers of hub_cls_kernel, verbatim
@@ -117,6 +152,7 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
     if (slot[d] < 0 || slot[d] >= L.xs_elems) return 3;
     xs[slot[d]] = x_row[d];
   }
+  for (int i = 0; i < 3; ++i) g_wave_a[i] = g_wave_b[i] = 0;
   if (spin) run_phases<true>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
   else run_phases<false>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
   for (i64 d = 0; d < num_dn; ++d) {
@@ -143,6 +179,10 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
         info[6 + 2 * ph] = mx; info[7 + 2 * ph] = tot;
       }
       info[10] = L.npieces;
+      // LDS.64 wavefronts of the phase bodies (x 1/1000), measured / conflict-free
+      info[11] = (int)(g_wave_a[0] / 1000); info[12] = (int)(g_wave_a[1] / 1000);
+      info[13] = (int)(g_wave_b[0] / 1000); info[14] = (int)(g_wave_b[1] / 1000);
+      info[15] = (int)(g_wave_a[2] + g_wave_b[2]);
     }
   }
   return 0;

@@ -50,7 +50,7 @@ def run_emu(lib, L, n_dn, bonds, width, u0, hop0, ups, eu, eng, x, spin=False, s
     s2 = np.ascontiguousarray([b[1] for b in bonds], dtype=np.int32)
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
-    info = np.zeros(12, dtype=np.int32)
+    info = np.zeros(16, dtype=np.int32)
     ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
     rc = lib.emu_cls_row(L, n_dn, len(bonds), s1.ctypes.data_as(ip), s2.ctypes.data_as(ip), width, 0.0, u0, hop0,
                          int(ups), eu, eng, int(spin), sd[0], sd[1], nwarps, x.ctypes.data_as(dp),
