@@ -338,15 +338,25 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
       for (; i < npos; ++i) {
         const uint32_t e = ent2[i];
         const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
+        double v0[T], v1[T];   // all loads of the pair first: 2 T shared-memory loads in flight per warp
 #pragma unroll
-        for (int t = 0; t < T; ++t) { ap[t] += cls_ld(xa[t] + e0); an[t] -= cls_ld(xa[t] + e1); }
+        for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
+#pragma unroll
+        for (int t = 0; t < T; ++t) v1[t] = cls_ld(xa[t] + e1);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { ap[t] += v0[t]; an[t] -= v1[t]; }
       }
 #pragma unroll 1
       for (; i < ntot; ++i) {
         const uint32_t e = ent2[i];
         const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
+        double v0[T], v1[T];
 #pragma unroll
-        for (int t = 0; t < T; ++t) { an[t] += cls_ld(xa[t] + e0); ap[t] -= cls_ld(xa[t] + e1); }
+        for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
+#pragma unroll
+        for (int t = 0; t < T; ++t) v1[t] = cls_ld(xa[t] + e1);
+#pragma unroll
+        for (int t = 0; t < T; ++t) { an[t] += v0[t]; ap[t] -= v1[t]; }
       }
     }
 #pragma unroll
@@ -357,11 +367,11 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
           const cls_addr xq = xs_a + (cls_addr)(w & 0x7fu) * 8u;
           const int sh = (w & 0x100u) ? 14 : 0;
           const uint32_t sgn = (w & 0x80u) << 24;   // parity of the dl part -> sign bit position
+          double v[T];
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const uint32_t e = lh[b][t];
-            ap[t] += cls_flip(cls_ld(xq + (cls_addr)((e >> sh) & 0x3fffu) * 8u), (e ^ sgn) & 0x80000000u);
-          }
+          for (int t = 0; t < T; ++t) v[t] = cls_ld(xq + (cls_addr)((lh[b][t] >> sh) & 0x3fffu) * 8u);
+#pragma unroll
+          for (int t = 0; t < T; ++t) ap[t] += cls_flip(v[t], (lh[b][t] ^ sgn) & 0x80000000u);
         }
       }
     }
@@ -413,15 +423,25 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
     for (; i < npos; ++i) {
       const uint32_t e = ent2[i];
       const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
+      double v0[T], v1[T];
 #pragma unroll
-      for (int t = 0; t < T; ++t) { hp[t] += cls_ld(q0 + 256u * t); hn[t] -= cls_ld(q1 + 256u * t); }
+      for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) v1[t] = cls_ld(q1 + 256u * t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) { hp[t] += v0[t]; hn[t] -= v1[t]; }
     }
 #pragma unroll 1
     for (; i < ntot; ++i) {
       const uint32_t e = ent2[i];
       const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
+      double v0[T], v1[T];
 #pragma unroll
-      for (int t = 0; t < T; ++t) { hn[t] += cls_ld(q0 + 256u * t); hp[t] -= cls_ld(q1 + 256u * t); }
+      for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) v1[t] = cls_ld(q1 + 256u * t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) { hn[t] += v0[t]; hp[t] -= v1[t]; }
     }
     const cls_addr yp = yl + (cls_addr)(jj * pk) * 8u;
 #pragma unroll

@@ -1,6 +1,7 @@
 // hubbard_op.cuh -- host-side operator object for the Hubbard / Anderson H.v (tables,
 // kernel selection, launches).
 #pragma once
+#include <stdlib.h>
 #include "hubbard.cuh"
 #include "hubbard_seg.cuh"
 #include "hubbard_cls.cuh"
@@ -45,6 +46,7 @@ struct HubbardOp : cmpy_op_s {
   ClsTables cls2;            // the same sector with the engine-2 table set (chunked tasks)
   LongTables lng2;           // long rows, engine 2
   int cls_engine = 0;        // engine the default (variant 0) class-major launches use: 0 or 2
+  int cls2_threads = 1024;   // CTA size of the engine-2 launches (512 / 768 / 1024)
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
@@ -213,9 +215,19 @@ struct HubbardOp : cmpy_op_s {
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
-    if (eng == 2) {  // engine 2: chunked tasks (1024-thread shapes only)
-      if (!p.with_up) hub_cls_kernel<LZ, 1024, 0, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
-      else hub_cls_kernel<LZ, 1024, 8, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
+    if (eng == 2) {  // engine 2: chunked tasks.  512 / 768-thread CTAs leave ptxas the registers to
+                     // keep several shared-memory loads of a hop list in flight per warp (at 64
+                     // registers it serialises every LDS -> DADD pair on one register)
+      if (cls2_threads == 512) {
+        if (!p.with_up) hub_cls_kernel<LZ, 512, 0, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
+        else hub_cls_kernel<LZ, 512, 16, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
+      } else if (cls2_threads == 768) {
+        if (!p.with_up) hub_cls_kernel<LZ, 768, 0, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
+        else hub_cls_kernel<LZ, 768, 12, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
+      } else {
+        if (!p.with_up) hub_cls_kernel<LZ, 1024, 0, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
+        else hub_cls_kernel<LZ, 1024, 8, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
+      }
       KERNEL_CHECK();
       return CMPY_OK;
     }
@@ -300,7 +312,19 @@ struct HubbardOp : cmpy_op_s {
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 1024, 0, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 12, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 768, 12, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 768, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 512, 16, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 512, 16, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 512, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 512, 0, false, false, 2>, smem_optin);
       if (rc) return rc;
+      if (const char* e = getenv("CMPY_CLS2_THREADS")) {
+        const int t = atoi(e);
+        if (t == 512 || t == 768 || t == 1024) cls2_threads = t;
+      }
       CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8, false, false, 2>, 1024, cls2.smem));
       if (nb < 1) cls2.release();
     }

@@ -106,6 +106,15 @@ if __name__ == "__main__":
     if mode == "ncu":
         ncu_launches()
         sys.exit(0)
+    if mode == "threads":  # engine 2 with 512 / 768 / 1024-thread CTAs and 16..64 work pieces
+        for nt, npc in ((512, 16), (512, 32), (512, 48), (768, 24), (768, 48), (1024, 32)):
+            os.environ["CMPY_CLS2_THREADS"] = str(nt)
+            os.environ["CMPY_CLS_PIECES"] = str(npc)
+            run(f"c4_square4x4_t{nt}_p{npc}", 16, square(4, 4), 8, 8, [9], [5, 9])
+        os.environ["CMPY_CLS2_THREADS"] = "512"
+        os.environ["CMPY_CLS_PIECES"] = "32"
+        run("chain16_t512_p32", 16, [[i, i + 1] for i in range(15)], 8, 8, [0, 9], [5, 9])
+        sys.exit(0)
     if mode == "pieces":   # engine 2 with different numbers of work pieces per phase
         for npc in (32, 48, 64, 96, 128):
             os.environ["CMPY_CLS_PIECES"] = str(npc)
