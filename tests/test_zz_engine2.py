@@ -137,3 +137,29 @@ def test_engine2_long_rows(cm, L, nu, nd, nbfn, kw):
         pytest.skip(f"engine 2 not available for this sector: {exc}")
     h.set_variant(0)
     assert float((got - ref).abs().max()) < HV_RTOL * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("N,s,periodic", [(18, 0, True), (20, 0, False), (22, 3, False)])
+def test_engine2_heisenberg(cm, N, s, periodic):
+    """Heisenberg fast path (sub-row launches of the class-major kernel, spin flavour) with
+    engine 2 (variant 9) against the generic row kernel (variant 1) and engine 0 (variant 5)."""
+    import torch
+    from cmpy_b200.models import HeisenbergModel
+    from refshim import ChainStandIn
+
+    h = HeisenbergModel(ChainStandIn(N, periodic=periodic), j=0.9, jz=1.1).hamilton_operator(s=s)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(h.shape[0], dtype=torch.float64, device="cuda", generator=g)
+    h.set_variant(1)
+    ref = h.matvec(x)
+    h.set_variant(5)
+    y0 = h.matvec(x)
+    try:
+        h.set_variant(9)
+        y2 = h.matvec(x)
+    except RuntimeError as exc:
+        h.set_variant(0)
+        pytest.skip(f"engine 2 not available for this spin sector: {exc}")
+    h.set_variant(0)
+    assert float((y0 - ref).abs().max() / ref.abs().max()) < HV_RTOL
+    assert float((y2 - ref).abs().max() / ref.abs().max()) < HV_RTOL
