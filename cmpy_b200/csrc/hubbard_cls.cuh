@@ -33,7 +33,8 @@
 
 #define CLS_MAX_CLS 12
 #define CLS2_MAX_PIECES 128   // engine 2: upper bound on the work pieces per phase
-#define CLS2_DEF_PIECES 64    // default: two pieces per warp of a 1024-thread CTA
+#define CLS2_DEF_PIECES 32    // default: one piece per warp of a 1024-thread CTA (measured: 32: 2.16 ms,
+                              // 64: 2.27 ms, 128: 2.46 ms on the 4x4 sector, dn-only pass)
 #define CLS_ZREG 96  // zero region appended to xs (target of HH list padding)
 
 struct ClsLayout {
@@ -295,6 +296,14 @@ CLS_HD void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
 //            (conflict-free) access and bonds whose source class does not exist are skipped
 //            for the whole warp.
 //   phase B  task = njj consecutive segments of one class, lanes along r: HH hops only.
+// Measured on B200 (4x4 sector, dn-only pass, profiles/r1_prof_cls_eng2_dn_c4.summary.txt,
+// profiles/r1_engine2_bench.jsonl): 5 % fewer issued instructions and 15 % fewer shared-memory
+// wavefronts than engine 0, same time (2.16 vs 2.12 ms; 512 / 768-thread CTAs, which let ptxas
+// keep several loads of a hop list in flight, are slower: 2.45 / 2.26 ms).  2/3 of the
+// instructions of both engines sit in the three hop loops themselves (LL 21 %, HH 19 %, LH 26 %),
+// not in the per-item headers this engine removes; engine 0 therefore stays the default and this
+// one is opt-in (variants 9 / 10, CMPY_CLS_ENGINE=2).  The phase bodies of both engines run lane
+// by lane on the CPU in tests/test_cls_emulation.py.
 // ---------------------------------------------------------------------------------
 template <int T, bool SPIN>
 CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* __restrict__ tab,
