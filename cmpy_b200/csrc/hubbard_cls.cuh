@@ -338,34 +338,28 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
     double ap[T], an[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
-    {  // LL hops: one list per (k, r), '+' pairs then '-' pairs
+    {  // LL hops: one list per (k, r), '+' entries then '-' entries (no padding)
       const uint32_t pp = ll_ptr[r];
-      const uint16_t* ent2 = reinterpret_cast<const uint16_t*>(ll_ent + (pp & 0xffffu));
+      const uint8_t* __restrict__ ent = ll_ent + (pp & 0xffffu);
       const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
       int i = 0;
 #pragma unroll 1
       for (; i < npos; ++i) {
-        const uint32_t e = ent2[i];
-        const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
-        double v0[T], v1[T];   // all loads of the pair first: 2 T shared-memory loads in flight per warp
+        const cls_addr e0 = (cls_addr)ent[i] * 8u;
+        double v0[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
 #pragma unroll
-        for (int t = 0; t < T; ++t) v1[t] = cls_ld(xa[t] + e1);
-#pragma unroll
-        for (int t = 0; t < T; ++t) { ap[t] += v0[t]; an[t] -= v1[t]; }
+        for (int t = 0; t < T; ++t) ap[t] += v0[t];
       }
 #pragma unroll 1
       for (; i < ntot; ++i) {
-        const uint32_t e = ent2[i];
-        const cls_addr e0 = (cls_addr)(e & 0xffu) * 8u, e1 = (cls_addr)(e >> 8) * 8u;
-        double v0[T], v1[T];
+        const cls_addr e0 = (cls_addr)ent[i] * 8u;
+        double v0[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
 #pragma unroll
-        for (int t = 0; t < T; ++t) v1[t] = cls_ld(xa[t] + e1);
-#pragma unroll
-        for (int t = 0; t < T; ++t) { an[t] += v0[t]; ap[t] -= v1[t]; }
+        for (int t = 0; t < T; ++t) an[t] += v0[t];
       }
     }
 #pragma unroll
@@ -426,31 +420,25 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
     double hp[T], hn[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) { hp[t] = 0.0; hn[t] = 0.0; }
-    const uint32_t* ent2 = reinterpret_cast<const uint32_t*>(hh_ent + (pp & 0xffffu));
+    const uint16_t* __restrict__ ent = hh_ent + (pp & 0xffffu);
     int i = 0;
 #pragma unroll 1
     for (; i < npos; ++i) {
-      const uint32_t e = ent2[i];
-      const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
-      double v0[T], v1[T];
+      const cls_addr q0 = xl + (cls_addr)ent[i] * 8u;
+      double v0[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
 #pragma unroll
-      for (int t = 0; t < T; ++t) v1[t] = cls_ld(q1 + 256u * t);
-#pragma unroll
-      for (int t = 0; t < T; ++t) { hp[t] += v0[t]; hn[t] -= v1[t]; }
+      for (int t = 0; t < T; ++t) hp[t] += v0[t];
     }
 #pragma unroll 1
     for (; i < ntot; ++i) {
-      const uint32_t e = ent2[i];
-      const cls_addr q0 = xl + (cls_addr)(e & 0xffffu) * 8u, q1 = xl + (cls_addr)(e >> 16) * 8u;
-      double v0[T], v1[T];
+      const cls_addr q0 = xl + (cls_addr)ent[i] * 8u;
+      double v0[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
 #pragma unroll
-      for (int t = 0; t < T; ++t) v1[t] = cls_ld(q1 + 256u * t);
-#pragma unroll
-      for (int t = 0; t < T; ++t) { hn[t] += v0[t]; hp[t] -= v1[t]; }
+      for (int t = 0; t < T; ++t) hn[t] += v0[t];
     }
     const cls_addr yp = yl + (cls_addr)(jj * pk) * 8u;
 #pragma unroll
@@ -859,6 +847,15 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
   // pack a ('+' list, '-' list) into pairs, each part padded to an even length with `dummy`
   auto pack = [&](const std::vector<uint16_t>& pos, const std::vector<uint16_t>& neg, uint16_t dummy,
                   auto& out, uint32_t& ptr) -> bool {
+    if (eng == 2) {  // engine 2: plain lists, no padding; the pointer counts entries, not pairs
+      const size_t start = out.size();
+      if (start >= 65536 || pos.size() + neg.size() > 255) return false;
+      typedef typename std::remove_reference<decltype(out)>::type::value_type E;
+      for (uint16_t v : pos) out.push_back((E)v);
+      for (uint16_t v : neg) out.push_back((E)v);
+      ptr = (uint32_t)start | ((uint32_t)pos.size() << 16) | ((uint32_t)(pos.size() + neg.size()) << 24);
+      return true;
+    }
     if (out.size() & 1) out.push_back(dummy);
     const size_t start = out.size();
     const size_t np2 = (pos.size() + 1) / 2, nn2 = (neg.size() + 1) / 2;
@@ -949,8 +946,8 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
     // into npieces contiguous pieces of about equal estimated cost; a piece that spans a class
     // boundary becomes several tasks.  Warp w of the CTA takes the pieces w, w + NW, ...
     // The cost model counts issued instructions of the compiled loops (SASS of sm_100a):
-    //   phase A, per column: 25 + (pairs + LH bonds) * (9 + 6 T) + 10 T     (T = 32-lane blocks)
-    //   phase B, per segment: 12 + pairs * (9 + 4 T) + 6 T
+    //   phase A, per column: 25 + entries * (5 + 3 T) + LH bonds * (9 + 8 T) + 10 T   (T = 32-lane blocks)
+    //   phase B, per segment: 12 + entries * (5 + 2 T) + 6 T
     int npieces = CLS2_DEF_PIECES;
     if (const char* e = getenv("CMPY_CLS_PIECES")) npieces = atoi(e);
     if (npieces < 1) npieces = 1;
@@ -992,12 +989,12 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
     auto cost_a = [&](int k, int r) {
       const int T = (L.H[k] + 31) / 32;
       const uint32_t pp = ll_ptr[L.qoff[k] + r];
-      return 25.0 + (double)((int)(pp >> 24) + L.nlh) * (9.0 + 6.0 * T) + 10.0 * T;
+      return 25.0 + (double)(pp >> 24) * (5.0 + 3.0 * T) + (double)L.nlh * (9.0 + 8.0 * T) + 10.0 * T;
     };
     auto cost_b = [&](int k, int jj) {
       const int T = (L.S[k] + 31) / 32;
       const uint32_t pp = hh_ptr[dh_list[L.hoff[k] + jj]];
-      return 12.0 + (double)(pp >> 24) * (9.0 + 4.0 * T) + 6.0 * T;
+      return 12.0 + (double)(pp >> 24) * (5.0 + 2.0 * T) + 6.0 * T;
     };
     partition(task_a, L.ptr_a, L.S, cost_a);   // lanes along jj (H_k), loop over r (S_k)
     partition(task_b, L.ptr_b, L.H, cost_b);   // lanes along r (S_k), loop over jj (H_k)
