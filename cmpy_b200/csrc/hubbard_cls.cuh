@@ -333,19 +333,26 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
 #pragma unroll
     for (int b = 0; b < CLS2_MAX_LH; ++b) lh[b][t] = b < nlh ? lhj[b * L.nseg + jj] : 0u;
   }
+  uint32_t pp_next = ll_ptr[r0];
 #pragma unroll 1
   for (int r = r0; r < r0 + nr; ++r) {
     double ap[T], an[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
-    {  // LL hops: one list per (k, r), '+' entries then '-' entries (no padding)
-      const uint32_t pp = ll_ptr[r];
+    {  // LL hops: one list per (k, r), '+' entries then '-' entries (no padding).  The entry of
+       // the next iteration and the list pointer of the next column are loaded one step ahead so
+       // that the dependent chain per hop is one shared-memory load, not two (the over-read by one
+       // element stays inside the table blob).
+      const uint32_t pp = pp_next;
+      pp_next = ll_ptr[r + 1];
       const uint8_t* __restrict__ ent = ll_ent + (pp & 0xffffu);
       const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
+      uint32_t e_next = ent[0];
       int i = 0;
 #pragma unroll 1
       for (; i < npos; ++i) {
-        const cls_addr e0 = (cls_addr)ent[i] * 8u;
+        const cls_addr e0 = (cls_addr)e_next * 8u;
+        e_next = ent[i + 1];
         double v0[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
@@ -354,7 +361,8 @@ CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned 
       }
 #pragma unroll 1
       for (; i < ntot; ++i) {
-        const cls_addr e0 = (cls_addr)ent[i] * 8u;
+        const cls_addr e0 = (cls_addr)e_next * 8u;
+        e_next = ent[i + 1];
         double v0[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
@@ -412,19 +420,23 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
   const uint16_t* __restrict__ hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
   const cls_addr xl = cls_base(xs) + (cls_addr)lane * 8u;
   const cls_addr yl = cls_base(ys) + (cls_addr)(L.xbase[k] + lane) * 8u;
+  uint32_t pp_next = hhp[jj0];
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + njj; ++jj) {
-    const uint32_t pp = hhp[jj];
+    const uint32_t pp = pp_next;
+    pp_next = hhp[jj + 1];
     const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
     if (ntot == 0) continue;
     double hp[T], hn[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) { hp[t] = 0.0; hn[t] = 0.0; }
     const uint16_t* __restrict__ ent = hh_ent + (pp & 0xffffu);
+    uint32_t e_next = ent[0];
     int i = 0;
 #pragma unroll 1
     for (; i < npos; ++i) {
-      const cls_addr q0 = xl + (cls_addr)ent[i] * 8u;
+      const cls_addr q0 = xl + (cls_addr)e_next * 8u;
+      e_next = ent[i + 1];
       double v0[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
@@ -433,7 +445,8 @@ CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ t
     }
 #pragma unroll 1
     for (; i < ntot; ++i) {
-      const cls_addr q0 = xl + (cls_addr)ent[i] * 8u;
+      const cls_addr q0 = xl + (cls_addr)e_next * 8u;
+      e_next = ent[i + 1];
       double v0[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
