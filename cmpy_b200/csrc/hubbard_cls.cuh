@@ -297,13 +297,17 @@ CLS_HD void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
 //            for the whole warp.
 //   phase B  task = njj consecutive segments of one class, lanes along r: HH hops only.
 // Measured on B200 (4x4 sector, dn-only pass, profiles/r1_prof_cls_eng2_dn_c4.summary.txt,
-// profiles/r1_engine2_bench.jsonl): 5 % fewer issued instructions and 15 % fewer shared-memory
-// wavefronts than engine 0, same time (2.16 vs 2.12 ms; 512 / 768-thread CTAs, which let ptxas
-// keep several loads of a hop list in flight, are slower: 2.45 / 2.26 ms).  2/3 of the
-// instructions of both engines sit in the three hop loops themselves (LL 21 %, HH 19 %, LH 26 %),
-// not in the per-item headers this engine removes; engine 0 therefore stays the default and this
-// one is opt-in (variants 9 / 10, CMPY_CLS_ENGINE=2).  The phase bodies of both engines run lane
-// by lane on the CPU in tests/test_cls_emulation.py.
+// profiles/r1_engine2_bench.jsonl).  First version (padded pair lists as in engine 0): 5 % fewer
+// issued instructions and 15 % fewer shared-memory wavefronts than engine 0 and the same time
+// (2.16 vs 2.12 ms); 512 / 768-thread CTAs, which let ptxas keep several loads of a hop list in
+// flight, are slower (2.45 / 2.26 ms).  2/3 of the instructions of both engines sit in the three
+// hop loops (LL 21 %, HH 19 %, LH 26 %), and the pass is bound by the latency of its dependent
+// shared-memory loads x 8 warps per scheduler rather than by issue slots (60 %) or the
+// shared-memory pipe (72-78 %).  With unpadded single-entry lists (2.12 ms) and the list entries /
+// pointers loaded one step ahead (2.05 ms; 16-site chain 1.54 vs 1.60 ms; 20-site slab 0.692 vs
+// 0.704 ms) it is 3-4 % ahead of engine 0.  Engine 0 stays the default this round; engine 2 is
+// opt-in (variants 9 / 10, CMPY_CLS_ENGINE=2).  The phase bodies of both engines run lane by lane
+// on the CPU in tests/test_cls_emulation.py.
 // ---------------------------------------------------------------------------------
 template <int T, bool SPIN>
 CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* __restrict__ tab,
