@@ -68,6 +68,8 @@ SIGNATURES = {
     "cmpy_hubbard_set_grid_limit": (c_int, [_p, c_int]),
     "cmpy_transpose_push": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                     POINTER(_p), _p]),
+    "cmpy_transpose_push_capped": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
+                                           POINTER(_p), c_int, _p]),
     "cmpy_transpose_pull_acc": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                         POINTER(_p), _p]),
 }

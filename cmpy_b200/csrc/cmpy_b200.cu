@@ -438,6 +438,14 @@ static int fill_peer_table(PeerTable& pt, int world, const int64_t* h_col_bounds
 API int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                             int64_t ld_t, int world, const int64_t* h_col_bounds,
                             void* const* h_peer_ptrs, void* stream) {
+  return cmpy_transpose_push_capped(d_x_slab, nrows, num_dn, row0, ld_t, world, h_col_bounds, h_peer_ptrs, 0,
+                                    stream);
+}
+
+API int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                                   int64_t ld_t, int world, const int64_t* h_col_bounds,
+                                   void* const* h_peer_ptrs, int max_ctas, void* stream) {
+  ARG_CHECK(max_ctas >= 0, "bad argument");
   ARG_CHECK(d_x_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
   PeerTable pt;
   int rc = fill_peer_table(pt, world, h_col_bounds, h_peer_ptrs);
@@ -445,7 +453,8 @@ API int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_d
   ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
   if (nrows == 0 || num_dn == 0) return CMPY_OK;
   const i64 ntiles = ((nrows + 127) / 128) * ((num_dn + 31) / 32);
-  const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  if (max_ctas > 0 && g > max_ctas) g = max_ctas;
   peer_transpose_kernel<false, 128><<<g, 256, 0, as_stream(stream)>>>(const_cast<double*>(d_x_slab), nrows,
                                                                       num_dn, row0, ld_t, pt);
   KERNEL_CHECK();

@@ -203,6 +203,13 @@ class ShardedHubbardOperator:
         import os
         self._sm_count = torch.cuda.get_device_properties(_lib.device()).multi_processor_count
         self._push_sms = int(os.environ.get("CMPY_PUSH_SMS", "32"))
+        # CMPY_PUSH_ORDER=dn_first (opt-in, not yet measured): enqueue the local dn pass first, on a
+        # high-priority stream, and cap the push grid at the CTAs that fit the reserved SMs.  With the
+        # default order the persistent push CTAs (8 per SM) are resident on every SM before the dn
+        # pass arrives, and a class-major CTA needs a whole SM's shared memory: at C5 the two phases
+        # serialise.
+        self._dn_first = os.environ.get("CMPY_PUSH_ORDER", "") == "dn_first"
+        self._hi = torch.cuda.Stream(priority=-1) if self._dn_first else None
 
     def _apply_local_peer(self, x_local, out, accumulate=False):
         torch = _lib.require_cuda()
@@ -213,6 +220,22 @@ class ShardedHubbardOperator:
         main = torch.cuda.current_stream()
         # every rank is done with the XT / YT slabs of the previous call
         self._h_xt.barrier(channel=0)
+        if self._dn_first and self.world > 1 and 0 < self._push_sms < self._sm_count:
+            ready = main.record_event()
+            self._hi.wait_event(ready)
+            with torch.cuda.stream(self._hi):
+                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, self._sm_count - self._push_sms),
+                           "cmpy_hubbard_set_grid_limit")
+                be.apply_rows(x_local, r0, nrows, out, accumulate=bool(accumulate))
+                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, 0), "cmpy_hubbard_set_grid_limit")
+            self._side.wait_event(ready)
+            with torch.cuda.stream(self._side):
+                _lib.check(L.cmpy_transpose_push_capped(_lib.ptr(x_local), nrows, nd, r0, nu, self.world, self._cb,
+                                                        self._peer_xt, 6 * self._push_sms, _lib.stream_ptr()),
+                           "cmpy_transpose_push_capped")
+            main.wait_stream(self._hi)
+            main.wait_stream(self._side)
+            return self._apply_second_half(out, r0, c0, nrows, ncols, nu, nd)
         # push the transposed tiles into the owners' XT slabs (side stream) under the local
         # diagonal + dn-hop pass (main stream)
         self._side.wait_stream(main)
@@ -227,6 +250,10 @@ class ShardedHubbardOperator:
             be.apply_rows(x_local, r0, nrows, out)
         _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, 0), "cmpy_hubbard_set_grid_limit")
         main.wait_stream(self._side)
+        return self._apply_second_half(out, r0, c0, nrows, ncols, nu, nd)
+
+    def _apply_second_half(self, out, r0, c0, nrows, ncols, nu, nd):
+        be, L = self.backend, _lib.lib()
         self._h_xt.barrier(channel=0)          # all pushes have landed
         be.apply_rows_t(self._xt, c0, ncols, self._yt)   # up hops, row-local in the dn-major slab
         self._h_yt.barrier(channel=0)          # every YT slab is complete

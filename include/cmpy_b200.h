@@ -207,6 +207,11 @@ int cmpy_hubbard_set_grid_limit(cmpy_op_t op, int max_ctas);
 int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                         int64_t ld_t, int world, const int64_t* h_col_bounds,
                         void* const* h_peer_ptrs, void* stream);
+/* cmpy_transpose_push with at most max_ctas persistent CTAs (0 = default grid): lets the push run
+ * on the few SMs the caller keeps free of the local dn pass instead of spreading over all of them. */
+int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
+                               int64_t ld_t, int world, const int64_t* h_col_bounds,
+                               void* const* h_peer_ptrs, int max_ctas, void* stream);
 int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                             int64_t ld_t, int world, const int64_t* h_col_bounds,
                             void* const* h_peer_ptrs, void* stream);
