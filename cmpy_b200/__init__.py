@@ -22,6 +22,6 @@ from .operators import (  # noqa: E402
     AnnihilationOperator,
 )
 from .models.abc import ModelParameters, AbstractModel, AbstractManyBodyModel  # noqa: E402
-from . import models, exactdiag, greens, dmft  # noqa: E402
+from . import models, exactdiag, greens, dmft, observables  # noqa: E402
 
 __version__ = "0.1.0"

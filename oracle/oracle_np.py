@@ -569,3 +569,27 @@ def chain_neighbor_lists(num_sites, periodic=False):
         else:
             out.append([k for k in (i - 1, i + 1) if 0 <= k < num_sites])
     return out
+
+
+# ---------------------------------------------------------------------------
+# spin observables (reference: scripts/heisenberg.py)
+# ---------------------------------------------------------------------------
+
+def sz_expval(states, gs, pos=0):
+    """`sz_expval` (scripts/heisenberg.py:50-57): sum of a^2 * (+1/2 if bit `pos` set else -1/2)."""
+    sz = 0.0
+    for ai, si in zip(gs, states):
+        b = (int(si) >> pos) & 1
+        sz += (-1) ** (b + 1) / 2 * ai * ai
+    return sz
+
+
+def sz_correl(states, gs, delta, j=1.0, pos=0):
+    """`sz_correl` (scripts/heisenberg.py:131-138, there with pos = 0): sum of a^2 * sign * j / 4,
+    sign +1 when the bits at `pos` and `pos + delta` are equal."""
+    res = 0.0
+    for ai, si in zip(gs, states):
+        b1 = (int(si) >> pos) & 1
+        b2 = (int(si) >> (pos + delta)) & 1
+        res += ai * ai * (-1) ** b1 * (-1) ** b2 * j / 4
+    return res

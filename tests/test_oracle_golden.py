@@ -279,3 +279,28 @@ def test_realtime_gf_oracle_vs_reference(L, pos):
         out = orc.gf_realtime_dense(L, nb, 4.0, -2.0, 1.0, n_up, n_dn, float(g[key + "_gs_energy"]),
                                     g[key + "_gs_state"], g[key + "_times"], pos, greater)
         assert np.abs(out - g[key + name]).max() < 1e-10
+
+
+def test_sz_correlator_is_the_diagonal_of_a_one_pair_ising_model():
+    """The identity cmpy_b200/observables.py rests on: the diagonal of the reference's Heisenberg
+    Hamiltonian with the single directed pair (i, j), j = 0, jz = 1 is Sz_i Sz_j
+    (cmpy/models/heisenberg.py:28-31), so scripts/heisenberg.py's sz_correl is a weighted sum of it."""
+    N, s = 8, 0
+    states = orc.spin_states(N, s)
+    rng = np.random.default_rng(2)
+    gs = rng.standard_normal(len(states))
+    gs /= np.linalg.norm(gs)
+    for i, j in [(0, 3), (5, 2), (0, 7)]:
+        nbl = [[] for _ in range(N)]
+        nbl[i] = [j]
+        r, c, v = orc.heisenberg_triplets(states, nbl, j=0.0, jz=1.0)
+        diag = np.zeros(len(states))
+        np.add.at(diag, r[r == c], v[r == c])
+        assert set(np.round(diag, 12)) <= {0.25, -0.25}
+        if i == 0:
+            assert abs(np.dot(gs * gs, diag) * 1.7 - orc.sz_correl(states, gs, j, j=1.7)) < 1e-14
+        else:
+            lo, d = min(i, j), abs(i - j)
+            assert abs(np.dot(gs * gs, diag) - orc.sz_correl(states, gs, d, pos=lo)) < 1e-14
+    # total magnetisation: sum_k <Sz_k> = s
+    assert abs(sum(orc.sz_expval(states, gs, k) for k in range(N)) - s) < 1e-13

@@ -1,0 +1,62 @@
+"""GPU parity of the spin observables (cmpy_b200/observables.py)
+against the restatement of scripts/heisenberg.py's helpers in oracle/oracle_np.py."""
+import numpy as np
+import pytest
+
+import oracle_np as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import cmpy_b200
+
+    return cmpy_b200
+
+
+@pytest.mark.parametrize("N,s", [(8, 0), (10, 1), (12, 0), (18, 0)])
+def test_sz_observables_vs_oracle(cm, N, s):
+    from cmpy_b200 import observables as obs
+
+    states = orc.spin_states(N, s)
+    rng = np.random.default_rng(N)
+    gs = rng.standard_normal(len(states))
+    gs /= np.linalg.norm(gs)
+    for pos in (0, N // 2, N - 1):
+        assert abs(obs.sz_expval(N, s, gs, pos) - orc.sz_expval(states, gs, pos)) < 1e-13
+    for delta in (1, 2, N - 1):
+        assert abs(obs.sz_correl(N, s, gs, delta, j=1.3) - orc.sz_correl(states, gs, delta, j=1.3)) < 1e-13
+    assert abs(obs.sz_correl(N, s, gs, 3, pos=2) - orc.sz_correl(states, gs, 3, pos=2)) < 1e-13
+    corr = obs.spin_correlations(N, s, gs, pos=1)
+    ref = [0.25 if k == 1 else orc.sz_correl(states, gs, abs(k - 1), pos=min(k, 1)) for k in range(N)]
+    assert np.abs(corr - np.asarray(ref)).max() < 1e-13
+    # sum rule: sum_k <Sz_1 Sz_k> = s <Sz_1>
+    assert abs(corr.sum() - s * obs.sz_expval(N, s, gs, 1)) < 1e-12
+    with pytest.raises(ValueError):
+        obs.sz_expval(N + 1, 0, gs, 0)
+
+
+def test_ground_state_correlations_heisenberg_chain(cm):
+    """Antiferromagnetic chain: the ground-state correlations alternate in sign and
+    3 * sum over bonds of <Sz_i Sz_{i+1}> * (j / 2 scale of the reference) reproduces E0 (SU(2) symmetry)."""
+    from cmpy_b200.exactdiag import lanczos_run
+    from cmpy_b200.models import HeisenbergModel
+    from cmpy_b200 import observables as obs
+    from refshim import ChainStandIn
+
+    N = 12
+    model = HeisenbergModel(ChainStandIn(N), j=1.0, jz=1.0)
+    h = model.hamilton_operator(s=0)
+    res = lanczos_run(h, None, maxit=400, tol=1e-13, resid_tol=1e-10, want_vector=True)
+    assert abs(res.e0 - (-5.903591587651)) < 1e-9
+    gs = res.vector
+    c = obs.spin_correlations(N, 0, gs, pos=0)
+    assert c[0] == 0.25 and c[1] < 0 < c[2] and c[3] < 0
+    # H = sum over bonds of 2*(jz/4)*4 Sz Sz ... in the reference scaling a bond contributes
+    # (jz / 2) * 4 <Sz Sz> / 2 = 2 jz <Sz_i Sz_j> to the diagonal part; isotropy: E0 = 3 * diagonal part
+    zz = sum(obs.sz_correl(N, 0, gs, 1, pos=i) for i in range(N - 1))
+    assert abs(3.0 * 2.0 * zz - res.e0) < 1e-8
