@@ -24,6 +24,12 @@ OUT = os.path.join(HERE, "emu", "_build", "libcls_emu.so")
 
 
 def _build():
+    import shutil
+
+    if shutil.which("nvcc") is None:
+        if os.path.exists(OUT):
+            return OUT   # prebuilt by __graft_entry__.build()
+        pytest.skip("nvcc not available to build the emulation harness")
     deps = [SRC] + [os.path.join(ROOT, "cmpy_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "cmpy_b200", "csrc"))
                     if f.endswith(".cuh")]
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
