@@ -517,7 +517,6 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   const uint32_t* ll_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_ll_ptr);
   const uint8_t* ll_ent = tab + L.off_ll_ent;
   const uint16_t* dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list);
-  const uint16_t* hi_goff = reinterpret_cast<const uint16_t*>(tab + L.off_hi_goff);
   const uint16_t* hi_sbase = reinterpret_cast<const uint16_t*>(tab + L.off_hi_sbase);
   const uint8_t* hi_k = tab + L.off_hi_k;
   const uint32_t* hh_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_hh_ptr);

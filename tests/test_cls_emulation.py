@@ -10,6 +10,7 @@ import ctypes
 import os
 import subprocess
 import sys
+import zlib
 
 import numpy as np
 import pytest
@@ -132,7 +133,7 @@ CASES = [
 @pytest.mark.parametrize("name,L,n_dn,bonds", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("eng", [0, 2])
 def test_hubbard_row(emu, name, L, n_dn, bonds, eng):
-    rng = np.random.default_rng(hash(name) % 1000)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
     num = len(orc.enumerate_states(L, n_dn))
     x = rng.standard_normal(num)
     ups = int(rng.integers(0, 1 << L))
