@@ -210,6 +210,9 @@ class ShardedHubbardOperator:
         # serialise.
         self._dn_first = os.environ.get("CMPY_PUSH_ORDER", "") == "dn_first"
         self._hi = torch.cuda.Stream(priority=-1) if self._dn_first else None
+        # CMPY_PULL_PARTS=k (opt-in, not yet measured): the up pass runs in k chunks of the owned
+        # dn-columns and the pull of chunk i overlaps the up pass of chunk i + 1
+        self._pull_parts = max(1, int(os.environ.get("CMPY_PULL_PARTS", "1")))
 
     def _apply_local_peer(self, x_local, out, accumulate=False):
         torch = _lib.require_cuda()
@@ -252,7 +255,36 @@ class ShardedHubbardOperator:
         main.wait_stream(self._side)
         return self._apply_second_half(out, r0, c0, nrows, ncols, nu, nd)
 
+    def _apply_second_half_chunked(self, out, r0, c0, nrows, ncols, nu, nd):
+        """Up pass in ``_pull_parts`` chunks; chunk i is pulled (side stream, capped grid) while
+        chunk i + 1 is computed (main stream, grid capped to leave SMs to the pull)."""
+        torch = _lib.require_cuda()
+        be, L = self.backend, _lib.lib()
+        parts = self._pull_parts
+        main, side = torch.cuda.current_stream(), self._side
+        self._h_xt.barrier(channel=0)          # all pushes have landed
+        reserve = self._push_sms if 0 < self._push_sms < self._sm_count else 0
+        for k in range(parts):
+            lo, hi = ncols * k // parts, ncols * (k + 1) // parts   # same split as the kernel's
+            if hi > lo:
+                limit = self._sm_count - reserve if (k > 0 and reserve) else 0
+                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_t.handle, limit), "cmpy_hubbard_set_grid_limit")
+                be.apply_rows_t(self._xt[lo * nu:], c0 + lo, hi - lo, self._yt[lo * nu:])
+                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_t.handle, 0), "cmpy_hubbard_set_grid_limit")
+            done = main.record_event()
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                self._h_yt.barrier(channel=1)  # chunk k of every YT slab is complete
+                _lib.check(L.cmpy_transpose_pull_acc_part(_lib.ptr(out), nrows, nd, r0, nu, self.world, self._cb,
+                                                          self._peer_yt, k, parts,
+                                                          6 * reserve if k + 1 < parts else 0,
+                                                          _lib.stream_ptr()), "cmpy_transpose_pull_acc_part")
+        main.wait_stream(side)
+        return out
+
     def _apply_second_half(self, out, r0, c0, nrows, ncols, nu, nd):
+        if self._pull_parts > 1 and self.world > 1:
+            return self._apply_second_half_chunked(out, r0, c0, nrows, ncols, nu, nd)
         be, L = self.backend, _lib.lib()
         self._h_xt.barrier(channel=0)          # all pushes have landed
         be.apply_rows_t(self._xt, c0, ncols, self._yt)   # up hops, row-local in the dn-major slab
