@@ -13,6 +13,8 @@
 #include <cmath>
 
 static long long g_wave_a[3], g_wave_b[3];   // wavefronts, ideal wavefronts, divergent tasks
+static int g_emu_shift = 0;
+extern "C" void emu_set_shift(int shift) { g_emu_shift = shift ? 1 : 0; }
 
 template <bool SPIN>
 static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<double>& xs,
@@ -140,13 +142,23 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
   std::vector<double> xs(xs_total, 0.0), ys(L.xs_elems, std::nan(""));
   const int16_t* seg_delta = reinterpret_cast<const int16_t*>(H.blob.data() + L.off_seg_delta);
-  const int npairs = (int)(num_dn / 2);
+  // the column-pair -> slot map of hub_cls_kernel: shift = 0 pairs (2i, 2i+1); shift = 1 (sub-rows of
+  // long rows that start at an odd element of the vector) pairs (2i-1, 2i) with one-column pairs at
+  // both ends
+  const int shift = g_emu_shift, ndi = (int)num_dn;
+  const int npairs = (ndi + shift + 1) / 2;
+  const std::vector<uint16_t>& pseg = shift ? H.pair_seg1 : H.pair_seg;
+  if ((int)pseg.size() < npairs) return 3;
   std::vector<int> slot(num_dn, -1);
-  for (int pi = 0; pi < npairs; ++pi) {   // the staging loop of hub_cls_kernel (shift = 0)
-    const uint32_t ps = H.pair_seg[pi];
-    const int si = (int)(ps & 0x7fffu), d = 2 * pi;
-    slot[d] = d + seg_delta[si];
-    slot[d + 1] = d + 1 + seg_delta[si + (int)(ps >> 15)];
+  for (int pi = 0; pi < npairs; ++pi) {
+    const uint32_t ps = pseg[pi];
+    const int si = (int)(ps & 0x7fffu), d = 2 * pi - shift;
+    int slot0 = d + seg_delta[si];
+    int slot1 = d + 1 + seg_delta[si + (int)(ps >> 15)];
+    if (d < 0) slot0 = slot1;
+    if (d + 1 >= ndi) slot1 = slot0;
+    if (d >= 0) slot[d] = slot0;
+    if (d + 1 < ndi) slot[d + 1] = slot1;
   }
   for (i64 d = 0; d < num_dn; ++d) {
     if (slot[d] < 0 || slot[d] >= L.xs_elems) return 3;

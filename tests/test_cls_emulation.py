@@ -209,3 +209,20 @@ def test_spin_flavour_row(emu, name, L, n, bonds, eng):
     assert rc == 0
     ref = direct_row(L, n, bonds, 0, 0.0, 0.5, 0, 0.0, x, spin=True, sd=sd)
     assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("eng", [0, 2])
+@pytest.mark.parametrize("L,n,bonds", [(16, 8, chain(16)), (16, 6, chain(16)), (12, 6, ring(12))], ids=["c16n8", "c16n6", "r12"])
+def test_shifted_column_pairs(emu, eng, L, n, bonds):
+    """Sub-rows of long rows that start at an odd element use the column pairs (2i-1, 2i) and the
+    second pair table (pair_seg1): the slot map must still cover every column exactly once."""
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal(len(orc.enumerate_states(L, n)))
+    emu.emu_set_shift(1)
+    try:
+        rc, y, _ = run_emu(emu, L, n, bonds, L, 4.0, 1.0, 0b0110100110010110 & ((1 << L) - 1), -2.0, eng, x)
+    finally:
+        emu.emu_set_shift(0)
+    assert rc == 0, rc
+    ref = direct_row(L, n, bonds, L, 4.0, 1.0, 0b0110100110010110 & ((1 << L) - 1), -2.0, x)
+    assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
