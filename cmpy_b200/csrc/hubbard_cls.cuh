@@ -1178,10 +1178,26 @@ static int upload_vec(T*& dptr, const std::vector<T>& v) {
 
 // `skipped` (optional): popcounts of the top bits whose sub-rows the class-major kernel cannot
 // take (odd length ...); without it such a sector makes the whole table set unavailable.
+// Host mirror of the long-row tables (tests/emu only): with `mirror` set, build_long_tables makes no
+// CUDA call and leaves every table in host vectors instead of uploading it.
+struct LongSetHost {
+  ClsHost cls;
+  int pt = 0, ntop = 0, row_len = 0, shift = 0;
+  std::vector<uint32_t> top_val, sb_map;
+  std::vector<int> sub_off, tb_ptr;
+  std::vector<int2> tb_ent, sb_src;
+};
+struct LongHost {
+  std::vector<LongSetHost> sets;
+  int nsb = 0;
+  double e_dn_const = 0.0;
+};
+
 static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                              const int* s1, const int* s2, int sign_width, const double* eps,
-                             i64 smem_optin, std::vector<int>* skipped = nullptr, int eng = 0) {
-  T.release();
+                             i64 smem_optin, std::vector<int>* skipped = nullptr, int eng = 0,
+                             LongHost* mirror = nullptr) {
+  if (!mirror) T.release();
   const u64* B = host_binom();
   const int R = LONG_RBITS, tb = num_sites - R;
   if (tb < 1 || tb > 16 || n_dn < 0 || n_dn > num_sites) return CMPY_OK;
@@ -1216,10 +1232,20 @@ static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn,
     LongSet S;
     S.pt = pt;
     S.row_len = (int)B[R * BINOM_N + nr];
-    int rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
-                              eps, smem_optin, eng);
+    LongSetHost HS;
+    int rc;
+    bool cls_ok;
+    if (mirror) {
+      rc = build_cls_host(HS.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
+                          eps, smem_optin, eng);
+      cls_ok = HS.cls.ok;
+    } else {
+      rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
+                            eps, smem_optin, eng);
+      cls_ok = S.cls.ok;
+    }
     if (rc) { S.release(); return rc; }
-    if (!S.cls.ok) {
+    if (!cls_ok) {
       S.release();
       if (skipped) { skipped->push_back(pt); continue; }
       T.release();
@@ -1298,6 +1324,14 @@ static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn,
             sb_map[((size_t)q * 2 + dir) * S.row_len + r] = e;
           }
       }
+    }
+    if (mirror) {
+      HS.pt = pt; HS.ntop = S.ntop; HS.row_len = S.row_len; HS.shift = S.shift;
+      HS.top_val = top_val; HS.sub_off = so; HS.tb_ptr = tb_ptr; HS.tb_ent = tb_ent;
+      HS.sb_src = sb_src; HS.sb_map = sb_map;
+      mirror->nsb = T.nsb; mirror->e_dn_const = T.e_dn_const;
+      mirror->sets.push_back(std::move(HS));
+      continue;
     }
     rc = upload_vec(S.d_top_val, top_val);
     if (!rc) rc = upload_vec(S.d_sub_off, so);

@@ -199,3 +199,80 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// Long rows (more than 16 sites): one dn row through the sub-row launches of hub_cls_kernel<..., LONG>.
+// Tables come from build_long_tables in host-mirror mode (the builder the library uses); staging and
+// the long-row part of phase C (top-bond sub-row gathers, straddling-bond index maps) restate the
+// kernel lines.  `covered` marks the columns whose sub-row class the kernel takes (odd-length classes
+// are left to another kernel and stay 0).
+extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, const int* s2,
+                            int sign_width, double u0, double hop0, unsigned ups, double eu, int eng,
+                            const double* x_row, double* y_row, unsigned char* covered) {
+  const u64* B = host_binom();
+  if (num_sites <= LONG_RBITS || num_sites > 32 || n_dn < 0 || n_dn > num_sites) return 2;
+  const i64 num_dn = (i64)B[num_sites * BINOM_N + n_dn];
+  LongTables dummy;
+  LongHost LH;
+  std::vector<int> skipped;
+  const double eps[1] = {0.0};
+  if (build_long_tables(dummy, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448, &skipped, eng, &LH))
+    return 2;
+  if (LH.sets.empty()) return 1;
+  SpinDiag sd;
+  memset(&sd, 0, sizeof(sd));
+  for (i64 d = 0; d < num_dn; ++d) { y_row[d] = 0.0; covered[d] = 0; }
+  for (const LongSetHost& S : LH.sets) {
+    const ClsLayout& L = S.cls.lay;
+    const int ndi = S.row_len, shift = S.shift;
+    const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
+    const int16_t* seg_delta = reinterpret_cast<const int16_t*>(S.cls.blob.data() + L.off_seg_delta);
+    const std::vector<uint16_t>& pseg = shift ? S.cls.pair_seg1 : S.cls.pair_seg;
+    const int npairs = (ndi + shift + 1) / 2;
+    if ((int)pseg.size() < npairs) return 3;
+    std::vector<int> slot(ndi, -1);
+    for (int pi = 0; pi < npairs; ++pi) {
+      const uint32_t ps = pseg[pi];
+      const int si = (int)(ps & 0x7fffu), d = 2 * pi - shift;
+      int slot0 = d + seg_delta[si];
+      int slot1 = d + 1 + seg_delta[si + (int)(ps >> 15)];
+      if (d < 0) slot0 = slot1;
+      if (d + 1 >= ndi) slot1 = slot0;
+      if (d >= 0) slot[d] = slot0;
+      if (d + 1 < ndi) slot[d + 1] = slot1;
+    }
+    for (int ti = 0; ti < S.ntop; ++ti) {
+      const uint32_t dtop = S.top_val[ti];
+      const i64 base = S.sub_off[ti];
+      if ((int)(base & 1) != shift) return 4;   // the 16-byte alignment rule of the launch
+      const double* xr = x_row + base;
+      std::vector<double> xs(xs_total, 0.0), ys(L.xs_elems, std::nan(""));
+      for (int d = 0; d < ndi; ++d) {
+        if (slot[d] < 0 || slot[d] >= L.xs_elems) return 3;
+        xs[slot[d]] = xr[d];
+      }
+      const double eu_sub = eu + LH.e_dn_const + u0 * (double)__builtin_popcount((ups >> 16) & dtop);
+      run_phases<false>(S.cls, sd, xs, ys, ups, eu_sub, u0, hop0, 32);
+      for (int d = 0; d < ndi; ++d) {
+        double a = ys[slot[d]];
+        if (std::isnan(a)) return 3;
+        for (int q = S.tb_ptr[ti]; q < S.tb_ptr[ti + 1]; ++q)   // hops inside dtop: whole sub-row gathers
+          a += (S.tb_ent[q].y ? -hop0 : hop0) * xr[d + S.tb_ent[q].x];
+        for (int sb = 0; sb < LH.nsb; ++sb) {                   // bonds straddling site 15 | 16
+          const int2 src = S.sb_src[(size_t)sb * S.ntop + ti];
+          if (src.y & 1) {
+            const uint32_t e0 = S.sb_map[((size_t)(2 * sb + ((src.y >> 1) & 1))) * ndi + d];
+            const uint32_t ptop = (uint32_t)(src.y >> 2) & 1u;
+            if (e0 >> 31) {
+              const double v = hop0 * xr[src.x + (i64)(e0 & 0x3fffffffu)];
+              a += (((e0 >> 30) & 1u) ^ ptop) ? -v : v;
+            }
+          }
+        }
+        y_row[base + d] = a;
+        covered[base + d] = 1;
+      }
+    }
+  }
+  return 0;
+}

@@ -226,3 +226,49 @@ def test_shifted_column_pairs(emu, eng, L, n, bonds):
     assert rc == 0, rc
     ref = direct_row(L, n, bonds, L, 4.0, 1.0, 0b0110100110010110 & ((1 << L) - 1), -2.0, x)
     assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def run_long(lib, L, n_dn, bonds, width, u0, hop0, ups, eu, eng, x):
+    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    lib.emu_long_row.restype = ctypes.c_int
+    lib.emu_long_row.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, ctypes.c_int, ctypes.c_double,
+                                 ctypes.c_double, ctypes.c_uint, ctypes.c_double, ctypes.c_int, dp, dp,
+                                 ctypes.POINTER(ctypes.c_ubyte)]
+    s1 = np.ascontiguousarray([b[0] for b in bonds], dtype=np.int32)
+    s2 = np.ascontiguousarray([b[1] for b in bonds], dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    cov = np.zeros(len(x), dtype=np.uint8)
+    rc = lib.emu_long_row(L, n_dn, len(bonds), s1.ctypes.data_as(ip), s2.ctypes.data_as(ip), width, u0, hop0,
+                          int(ups), eu, eng, x.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                          cov.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    return rc, y, cov.astype(bool)
+
+
+LONG_CASES = [
+    ("chain17_n8", 17, 8, chain(17)),
+    ("ring17_n5", 17, 5, ring(17)),
+    ("lattice3x6_n9", 18, 9, square(6, 3)),
+    ("chain19_n9_extra", 19, 9, chain(19) + [(3, 17), (12, 18), (16, 18)]),
+    ("chain20_n4", 20, 4, chain(20)),
+]
+
+
+@pytest.mark.parametrize("name,L,n_dn,bonds", LONG_CASES, ids=[c[0] for c in LONG_CASES])
+@pytest.mark.parametrize("eng", [0, 2])
+def test_long_row(emu, name, L, n_dn, bonds, eng):
+    """Rows of more than 16 sites (BASELINE config C5 is the 20-site chain): the tables of
+    build_long_tables (sub-rows by the top bits, top-bond gather lists, straddling-bond index maps)
+    and the sub-row passes reproduce (D + T_dn) x on every column the class-major kernel takes."""
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    num = len(orc.enumerate_states(L, n_dn))
+    x = rng.standard_normal(num)
+    ups = int(rng.integers(0, 1 << L))
+    u0, hop0, eu = 4.0, 1.0, -1.5
+    rc, y, cov = run_long(emu, L, n_dn, bonds, L, u0, hop0, ups, eu, eng, x)
+    if rc == 1:
+        pytest.skip("no sub-row class of this sector fits the class-major kernel")
+    assert rc == 0, rc
+    assert cov.any()
+    ref = direct_row(L, n_dn, bonds, L, u0, hop0, ups, eu, x)
+    assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max())
