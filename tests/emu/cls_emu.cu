@@ -206,6 +206,12 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
 // the long-row part of phase C (top-bond sub-row gathers, straddling-bond index maps) restate the
 // kernel lines.  `covered` marks the columns whose sub-row class the kernel takes (odd-length classes
 // are left to another kernel and stay 0).
+static int g_long_spin = 0;           // 1: XXZ flavour (hub_cls_kernel<..., LONG, SPIN> as launched by heisenberg.cuh)
+static double g_long_sd[2] = {0, 0};  // e0, escale of the spin diagonal
+extern "C" void emu_long_set_spin(int spin, double e0, double escale) {
+  g_long_spin = spin; g_long_sd[0] = e0; g_long_sd[1] = escale;
+}
+
 extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, const int* s2,
                             int sign_width, double u0, double hop0, unsigned ups, double eu, int eng,
                             const double* x_row, double* y_row, unsigned char* covered) {
@@ -221,6 +227,19 @@ extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, 
   if (LH.sets.empty()) return 1;
   SpinDiag sd;
   memset(&sd, 0, sizeof(sd));
+  if (g_long_spin) {   // bonds grouped by site distance, as in HeisenbergOp::configure_fast
+    for (int k = 0; k < nbonds; ++k) {
+      const int delta = s2[k] - s1[k];
+      int i = 0;
+      for (; i < sd.ndelta; ++i) if (sd.delta[i] == delta) break;
+      if (i == sd.ndelta) {
+        if (sd.ndelta == 4) return 1;
+        sd.delta[sd.ndelta++] = delta;
+      }
+      sd.dmask[i] |= 1u << s1[k];
+    }
+    sd.e0 = g_long_sd[0]; sd.escale = g_long_sd[1];
+  }
   for (i64 d = 0; d < num_dn; ++d) { y_row[d] = 0.0; covered[d] = 0; }
   for (const LongSetHost& S : LH.sets) {
     const ClsLayout& L = S.cls.lay;
@@ -252,7 +271,8 @@ extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, 
         xs[slot[d]] = xr[d];
       }
       const double eu_sub = eu + LH.e_dn_const + u0 * (double)__builtin_popcount((ups >> 16) & dtop);
-      run_phases<false>(S.cls, sd, xs, ys, ups, eu_sub, u0, hop0, 32);
+      if (g_long_spin) run_phases<true>(S.cls, sd, xs, ys, dtop << 16, 0.0, 0.0, hop0, 32);
+      else run_phases<false>(S.cls, sd, xs, ys, ups, eu_sub, u0, hop0, 32);
       for (int d = 0; d < ndi; ++d) {
         double a = ys[slot[d]];
         if (std::isnan(a)) return 3;

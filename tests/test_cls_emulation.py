@@ -272,3 +272,28 @@ def test_long_row(emu, name, L, n_dn, bonds, eng):
     assert cov.any()
     ref = direct_row(L, n_dn, bonds, L, u0, hop0, ups, eu, x)
     assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name,N,n,bonds", [("xxz_chain18", 18, 9, chain(18)), ("xxz_ring18", 18, 8, ring(18)),
+                                             ("xxz_ladder2x10", 20, 10, square(2, 10)), ("xxz_chain22_n3", 22, 3, chain(22))],
+                         ids=["chain18", "ring18_n8", "ladder2x10", "chain22_n3"])
+@pytest.mark.parametrize("eng", [0, 2])
+def test_long_row_spin_flavour(emu, name, N, n, bonds, eng):
+    """The Heisenberg fast path (BASELINE config C3 is the 32-site chain): spin strings of more than
+    16 sites through the long-row tables with the spin diagonal."""
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    x = rng.standard_normal(len(orc.enumerate_states(N, n)))
+    dz = 0.5
+    sd = (dz * len(bonds), -2.0 * dz)
+    emu.emu_long_set_spin.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    emu.emu_long_set_spin(1, sd[0], sd[1])
+    try:
+        rc, y, cov = run_long(emu, N, n, bonds, 0, 0.0, 0.25, 0, 0.0, eng, x)
+    finally:
+        emu.emu_long_set_spin(0, 0.0, 0.0)
+    if rc == 1:
+        pytest.skip("no sub-row class of this sector fits the class-major kernel")
+    assert rc == 0, rc
+    assert cov.any()
+    ref = direct_row(N, n, bonds, 0, 0.0, 0.25, 0, 0.0, x, spin=True, sd=sd)
+    assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max())
