@@ -18,6 +18,7 @@
 //
 // ref for the matrix elements: cmpy/operators.py:305-527 (see hubbard.cuh).
 #pragma once
+#include <string.h>
 #include "common.cuh"
 #include "sector.cuh"
 #include "hubbard.cuh"
@@ -56,22 +57,43 @@ struct SegParams {
 struct __align__(16) UpEnt { i64 off; double coef; };
 
 // flip the sign of v when `neg` (0/1) is set, via the IEEE sign bit
-__device__ __forceinline__ double flip_sign(double v, uint32_t neg) {
+__host__ __device__ __forceinline__ double flip_sign(double v, uint32_t neg) {
+#ifdef __CUDA_ARCH__
   return __hiloint2double(__double2hiint(v) ^ (int)(neg << 31), __double2loint(v));
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  b ^= (unsigned long long)(neg & 1u) << 63;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
 }
 
+// seg_dn_part is __host__ __device__ so that tests/emu/cls_emu.cu can run it on the CPU against the
+// tables of build_seg_tables: shared-memory byte addresses are 32-bit shared-space addresses on the
+// device (identical code to the plain uint32_t version) and plain pointers on the host.
+#ifdef __CUDA_ARCH__
+typedef uint32_t seg_addr;
 __device__ __forceinline__ double lds_f64(uint32_t saddr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ int seg_popc(uint32_t v) { return __popc(v); }
+__device__ __forceinline__ int seg_ffs(uint32_t v) { return __ffs(v); }
+#else
+typedef uintptr_t seg_addr;
+inline double lds_f64(uintptr_t saddr) { return *reinterpret_cast<const double*>(saddr); }
+inline int seg_popc(uint32_t v) { return __builtin_popcount(v); }
+inline int seg_ffs(uint32_t v) { return __builtin_ffs((int)v); }
+#endif
 
 // All dn hops + diagonal of one amplitude (column d of the staged row).
 // Table entries hold BYTE offsets; every list is ordered "+ entries, then - entries" so no
 // per-hop sign arithmetic is needed (UNI). `xs_s` = shared-space address of xs[0].
 template <bool UNI>
-__device__ __forceinline__ double seg_dn_part(
-    const SegParams& sp, const unsigned char* tab, uint32_t xs_s, const double* s_hop,
+__host__ __device__ __forceinline__ double seg_dn_part(
+    const SegParams& sp, const unsigned char* tab, seg_addr xs_s, const double* s_hop,
     const double* s_u, uint32_t ups, double eu, int d, uint32_t dns, double xi) {
   const SegLayout& L = sp.lay;
   const uint8_t* lo_rank = tab + L.off_lo_rank;
@@ -84,17 +106,17 @@ __device__ __forceinline__ double seg_dn_part(
   const int dl = (int)(dns & (uint32_t)(L.nlo - 1));
   const int dh = (int)(dns >> L.m);
   const int r = lo_rank[dl];
-  const uint32_t seg_s = xs_s + (uint32_t)(d - r) * 8u;  // address of the segment start
-  const uint32_t r_s = xs_s + (uint32_t)r * 8u;          // xs + r
+  const seg_addr seg_s = xs_s + (uint32_t)(d - r) * 8u;  // address of the segment start
+  const seg_addr r_s = xs_s + (uint32_t)r * 8u;          // xs + r
   double diag;
   if (UNI) {
-    diag = eu + sp.e_dn_const + sp.hp.u0 * (double)__popc(ups & dns);
+    diag = eu + sp.e_dn_const + sp.hp.u0 * (double)seg_popc(ups & dns);
   } else {
     const double* e_lo = reinterpret_cast<const double*>(tab + L.off_e_lo);
     const double* e_hi = reinterpret_cast<const double*>(tab + L.off_e_hi);
     double w = 0.0;
     uint32_t both = ups & dns;
-    while (both) { const int i = __ffs(both) - 1; both &= both - 1; w += s_u[i]; }
+    while (both) { const int i = seg_ffs(both) - 1; both &= both - 1; w += s_u[i]; }
     diag = eu + (e_hi[dh] + e_lo[dl]) + w;
   }
   double acc = diag * xi;
@@ -292,7 +314,7 @@ static inline int align16(int x) { return (x + 15) & ~15; }
 // configuration is outside what the segment kernel supports (the caller falls back).
 static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                             const int* s1, const int* s2, int sign_width, const double* eps,
-                            bool uniform) {
+                            bool uniform, std::vector<unsigned char>* host_blob = nullptr) {
   T.ok = false;
   const u64* B = host_binom();
   if (n_dn < 0 || n_dn > num_sites) return CMPY_OK;
@@ -465,6 +487,11 @@ static int build_seg_tables(SegTables& T, int num_sites, int n_dn, i64 num_dn, i
   memcpy(&blob[L.off_lh_hi], lh_hi.data(), 4 * lh_hi.size());
   memcpy(&blob[L.off_e_lo], e_lo.data(), 8 * nlo);
   memcpy(&blob[L.off_e_hi], e_hi.data(), 8 * nhi);
+  if (host_blob) {  // tests/emu: keep the tables on the host, no CUDA call
+    *host_blob = blob;
+    T.ok = true;
+    return CMPY_OK;
+  }
   CU_CHECK(cudaMalloc(&T.d_blob, o));
   CU_CHECK(cudaMemcpy(T.d_blob, blob.data(), o, cudaMemcpyHostToDevice));
   T.ok = true;

@@ -296,3 +296,44 @@ extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, 
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// Segment kernel (hub_seg_kernel, the default full H.v): its per-amplitude device function
+// seg_dn_part<UNI> is __host__ __device__; here it runs for every column of one staged row against
+// the tables of build_seg_tables (host-mirror mode).  uniform = 1: one hop amplitude / U / eps
+// (template UNI); 0: per-bond hop, per-site U and eps.
+extern "C" int emu_seg_row(int num_sites, int n_dn, int nbonds, const int* s1, const int* s2,
+                           int sign_width, const double* hop, const double* u, const double* eps,
+                           int uniform, unsigned ups, double eu, const double* x_row, double* y_row) {
+  const u64* B = host_binom();
+  if (num_sites < 1 || num_sites > 20 || n_dn < 0 || n_dn > num_sites || nbonds > ELL_MAX_BONDS) return 2;
+  const i64 num_dn = (i64)B[num_sites * BINOM_N + n_dn];
+  SegTables T;
+  std::vector<unsigned char> blob;
+  if (build_seg_tables(T, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, uniform != 0, &blob)) return 2;
+  if (!T.ok) return 1;
+  std::vector<uint32_t> dn;   // ascending strings of popcount n_dn (Gosper)
+  if (n_dn == 0) dn.push_back(0);
+  else {
+    uint64_t v = (1ull << n_dn) - 1;
+    while (v < (1ull << num_sites)) {
+      dn.push_back((uint32_t)v);
+      const uint64_t c = v & (~v + 1), r = v + c;
+      v = (((r ^ v) >> 2) / c) | r;
+    }
+  }
+  if ((i64)dn.size() != num_dn) return 3;
+  SegParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.lay = T.lay; sp.e_dn_const = T.e_dn_const;
+  sp.hp.u0 = u[0]; sp.hp.hop0 = hop[0];
+  double s_u[32];
+  for (int i = 0; i < 32; ++i) s_u[i] = i < num_sites ? u[i] : 0.0;
+  std::vector<double> xs(x_row, x_row + num_dn);
+  const seg_addr xs_s = (seg_addr)xs.data();
+  for (i64 d = 0; d < num_dn; ++d) {
+    if (uniform) y_row[d] = seg_dn_part<true>(sp, blob.data(), xs_s, hop, s_u, ups, eu, (int)d, dn[d], xs[d]);
+    else y_row[d] = seg_dn_part<false>(sp, blob.data(), xs_s, hop, s_u, ups, eu, (int)d, dn[d], xs[d]);
+  }
+  return 0;
+}

@@ -297,3 +297,65 @@ def test_long_row_spin_flavour(emu, name, N, n, bonds, eng):
     assert cov.any()
     ref = direct_row(N, n, bonds, 0, 0.0, 0.25, 0, 0.0, x, spin=True, sd=sd)
     assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+def direct_row_general(L, n_dn, bonds, width, hop, u, eps, ups, eu, x):
+    """(D + T_dn) x for one row with per-bond hop amplitudes, per-site U and on-site energies."""
+    dn = np.asarray(orc.enumerate_states(L, n_dn), dtype=np.int64)
+    rank = {int(s): i for i, s in enumerate(dn)}
+    y = np.zeros_like(x)
+    for i, s in enumerate(dn):
+        s = int(s)
+        diag = eu + sum(eps[k] for k in range(L) if (s >> k) & 1) + sum(u[k] for k in range(L) if ((s & ups) >> k) & 1)
+        acc = 0.0
+        for b, (a, c) in enumerate(bonds):
+            if ((s >> a) & 1) == ((s >> c) & 1):
+                continue
+            between = sum(1 << k for k in range(a + 1, c) if k < width)
+            sign = -1.0 if bin(s & between).count("1") & 1 else 1.0
+            acc += sign * hop[b] * x[rank[s ^ (1 << a) ^ (1 << c)]]
+        y[i] = diag * x[i] + acc
+    return y
+
+
+SEG_CASES = [
+    ("chain8", 8, 4, chain(8)), ("ring10", 10, 5, ring(10)), ("sq4x3_n5", 12, 5, square(4, 3)),
+    ("chain12_n3", 12, 3, chain(12)), ("star12", 12, 6, [(0, j) for j in range(1, 12)]),
+    ("chain16", 16, 8, chain(16)), ("sq4x4", 16, 8, square(4, 4)), ("sq4x4_periodic", 16, 7, square(4, 4, True)),
+    ("chain5_n2", 5, 2, chain(5)),
+]
+
+
+@pytest.mark.parametrize("name,L,n_dn,bonds", SEG_CASES, ids=[c[0] for c in SEG_CASES])
+@pytest.mark.parametrize("uniform", [1, 0])
+@pytest.mark.parametrize("width_full", [True, False])
+def test_segment_kernel_dn_part(emu, name, L, n_dn, bonds, uniform, width_full):
+    """The per-amplitude device function of the default H.v kernel (hub_seg_kernel) on the CPU:
+    two-level (dh, dl) tables of build_seg_tables, uniform and site / bond dependent parameters,
+    with the fermion sign (width = L) and without (width = 0, Anderson convention)."""
+    rng = np.random.default_rng(zlib.crc32((name + str(uniform)).encode()))
+    num = len(orc.enumerate_states(L, n_dn))
+    x = rng.standard_normal(num)
+    ups = int(rng.integers(0, 1 << L))
+    width = L if width_full else 0
+    if uniform:
+        hop, u, eps = np.full(len(bonds), 0.8), np.full(L, 3.5), np.full(L, -0.3)
+    else:
+        hop, u, eps = rng.uniform(0.5, 1.5, len(bonds)), rng.uniform(0.0, 4.0, L), rng.uniform(-1.0, 1.0, L)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    emu.emu_seg_row.restype = ctypes.c_int
+    emu.emu_seg_row.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, ctypes.c_int, dp, dp, dp,
+                                ctypes.c_int, ctypes.c_uint, ctypes.c_double, dp, dp]
+    s1 = np.ascontiguousarray([b[0] for b in bonds], dtype=np.int32)
+    s2 = np.ascontiguousarray([b[1] for b in bonds], dtype=np.int32)
+    hop, u, eps = (np.ascontiguousarray(a, dtype=np.float64) for a in (hop, u, eps))
+    y = np.empty_like(x)
+    eu = 0.37
+    rc = emu.emu_seg_row(L, n_dn, len(bonds), s1.ctypes.data_as(ip), s2.ctypes.data_as(ip), width,
+                         hop.ctypes.data_as(dp), u.ctypes.data_as(dp), eps.ctypes.data_as(dp), uniform, ups, eu,
+                         x.ctypes.data_as(dp), y.ctypes.data_as(dp))
+    if rc == 1:
+        pytest.skip("sector outside the segment kernel")
+    assert rc == 0, rc
+    ref = direct_row_general(L, n_dn, bonds, width, hop, u, eps, ups, eu, x)
+    assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
