@@ -85,28 +85,45 @@ static int ensure_binom_uploaded() {  // once per device
 // ---------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------
+// (__host__ __device__: tests/emu runs the same functions on the CPU; the device code reads the
+// __constant__ table, the host code the table it was copied from.)
+__host__ __device__ __forceinline__ u64 binom_at(int n, int k) {
+#ifdef __CUDA_ARCH__
+  return c_binom[n][k];
+#else
+  return host_binom()[n * BINOM_N + k];
+#endif
+}
+__host__ __device__ __forceinline__ int ffs64(u64 v) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)v);
+#else
+  return __builtin_ffsll((long long)v);
+#endif
+}
+
 // colex (combinadic) rank of s among integers of the same popcount, ascending order.
-__device__ __forceinline__ i64 colex_rank(u64 s) {
+__host__ __device__ __forceinline__ i64 colex_rank(u64 s) {
   i64 r = 0;
   int k = 0;
   while (s) {
-    int p = __ffsll((long long)s) - 1;
+    int p = ffs64(s) - 1;
     s &= s - 1;
     ++k;
-    r += (i64)c_binom[p][k];
+    r += (i64)binom_at(p, k);
   }
   return r;
 }
 
 // inverse: the idx-th (0-based) integer with popcount n (any width up to 64 bits)
-__device__ __forceinline__ u64 colex_unrank(i64 idx, int n, int num_sites) {
+__host__ __device__ __forceinline__ u64 colex_unrank(i64 idx, int n, int num_sites) {
   u64 s = 0;
   u64 r = (u64)idx;
   int p = num_sites;
   for (int k = n; k >= 1; --k) {
-    do { --p; } while (c_binom[p][k] > r);
+    do { --p; } while (binom_at(p, k) > r);
     s |= (1ull << p);
-    r -= c_binom[p][k];
+    r -= binom_at(p, k);
   }
   return s;
 }

@@ -93,7 +93,7 @@ struct SiteValues {
   double v[64];
 };
 
-__device__ __forceinline__ double weighted_element_dev(u64 state, const SiteValues& sv) {
+__host__ __device__ __forceinline__ double weighted_element_dev(u64 state, const SiteValues& sv) {
   double value = 0.0;
   for (int i = 0; i < sv.n; ++i)
     if (state & (1ull << i)) value += sv.v[i];  // ascending site order, plain adds

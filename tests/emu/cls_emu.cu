@@ -337,3 +337,26 @@ extern "C" int emu_seg_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// K1 / K3 helpers (sector.cuh, common.cuh): the combinadic unrank / rank functions behind
+// cmpy_sector_enumerate / cmpy_sector_rank and the ascending-site energy sum behind
+// cmpy_weighted_elements, run on the CPU.
+extern "C" int emu_sector_enumerate(int num_sites, int n, long long first, long long count, long long* out) {
+  if (num_sites < 0 || num_sites > 64 || n < 0 || n > num_sites) return 2;
+  for (long long i = 0; i < count; ++i) out[i] = (long long)colex_unrank(first + i, n, num_sites);
+  return 0;
+}
+extern "C" int emu_sector_rank(const long long* states, long long count, long long* out) {
+  for (long long i = 0; i < count; ++i) out[i] = (long long)colex_rank((u64)states[i]);
+  return 0;
+}
+extern "C" int emu_weighted_elements(const long long* states, long long count, int nvals, const double* vals,
+                                     double* out) {
+  if (nvals < 0 || nvals > 64) return 2;
+  SiteValues sv;
+  sv.n = nvals;
+  for (int i = 0; i < nvals; ++i) sv.v[i] = vals[i];
+  for (long long i = 0; i < count; ++i) out[i] = weighted_element_dev((u64)states[i], sv);
+  return 0;
+}

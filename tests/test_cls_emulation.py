@@ -359,3 +359,56 @@ def test_segment_kernel_dn_part(emu, name, L, n_dn, bonds, uniform, width_full):
     assert rc == 0, rc
     ref = direct_row_general(L, n_dn, bonds, width, hop, u, eps, ups, eu, x)
     assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("L,n", [(4, 2), (8, 4), (10, 0), (10, 10), (12, 6), (16, 8), (20, 3), (31, 2), (40, 2), (62, 1), (63, 2)])
+def test_sector_unrank_rank(emu, L, n):
+    """K1: combinadic unrank / rank (colex order = ascending integers of fixed popcount,
+    cmpy/basis.py:655-666 and the bisect of cmpy/operators.py:276-299) on the CPU."""
+    llp = ctypes.POINTER(ctypes.c_longlong)
+    emu.emu_sector_enumerate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, llp]
+    emu.emu_sector_rank.argtypes = [llp, ctypes.c_longlong, llp]
+    ref = np.asarray(orc.enumerate_states(L, n), dtype=np.int64)
+    count = len(ref)
+    out = np.empty(count, dtype=np.int64)
+    assert emu.emu_sector_enumerate(L, n, 0, count, out.ctypes.data_as(llp)) == 0
+    np.testing.assert_array_equal(out.astype(np.uint64), ref.astype(np.uint64))
+    idx = np.empty(count, dtype=np.int64)
+    assert emu.emu_sector_rank(out.ctypes.data_as(llp), count, idx.ctypes.data_as(llp)) == 0
+    np.testing.assert_array_equal(idx, np.arange(count))
+
+
+def test_sector_unrank_window_of_the_c5_sector(emu):
+    """A window in the middle of C(20, 10) and the last strings of C(32, 16) (config C3)."""
+    llp = ctypes.POINTER(ctypes.c_longlong)
+    emu.emu_sector_enumerate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, llp]
+    emu.emu_sector_rank.argtypes = [llp, ctypes.c_longlong, llp]
+    for L, n, first in [(20, 10, 92378 - 50), (32, 16, 601080390 - 100)]:
+        out = np.empty(100, dtype=np.int64)
+        assert emu.emu_sector_enumerate(L, n, first, 100, out.ctypes.data_as(llp)) == 0
+        assert all(bin(int(v)).count("1") == n for v in out) and np.all(np.diff(out) > 0)
+        idx = np.empty(100, dtype=np.int64)
+        emu.emu_sector_rank(out.ctypes.data_as(llp), 100, idx.ctypes.data_as(llp))
+        np.testing.assert_array_equal(idx, first + np.arange(100))
+    assert int(out[-1]) == ((1 << 16) - 1) << 16      # the last Sz = 0 string of 32 sites
+
+
+def test_weighted_elements_bit_exact(emu):
+    """K3: sum over set bits in ascending site order (cmpy/operators.py:226-250); plain adds, so the
+    result is bit-identical to the Python loop."""
+    llp, dp = ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)
+    emu.emu_weighted_elements.argtypes = [llp, ctypes.c_longlong, ctypes.c_int, dp, dp]
+    rng = np.random.default_rng(8)
+    vals = rng.standard_normal(12)
+    states = np.asarray(orc.enumerate_states(12, 5), dtype=np.int64)
+    out = np.empty(len(states))
+    assert emu.emu_weighted_elements(states.ctypes.data_as(llp), len(states), 12, vals.ctypes.data_as(dp),
+                                     out.ctypes.data_as(dp)) == 0
+    ref = np.empty(len(states))
+    for i, s in enumerate(states):
+        v = 0.0
+        for k in range(12):
+            if (int(s) >> k) & 1:
+                v += vals[k]
+        ref[i] = v
+    np.testing.assert_array_equal(out, ref)
