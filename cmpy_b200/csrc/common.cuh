@@ -94,6 +94,13 @@ __host__ __device__ __forceinline__ u64 binom_at(int n, int k) {
   return host_binom()[n * BINOM_N + k];
 #endif
 }
+__host__ __device__ __forceinline__ int popc64(u64 v) {
+#ifdef __CUDA_ARCH__
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
 __host__ __device__ __forceinline__ int ffs64(u64 v) {
 #ifdef __CUDA_ARCH__
   return __ffsll((long long)v);
@@ -128,7 +135,7 @@ __host__ __device__ __forceinline__ u64 colex_unrank(i64 idx, int n, int num_sit
   return s;
 }
 
-__device__ __forceinline__ i64 bsearch_left(const i64* __restrict__ a, i64 n, i64 x) {
+__host__ __device__ __forceinline__ i64 bsearch_left(const i64* __restrict__ a, i64 n, i64 x) {
   i64 lo = 0, hi = n;
   while (lo < hi) {
     i64 mid = (lo + hi) >> 1;
