@@ -202,6 +202,25 @@ def workload_config(workload, n_gpus):
     }
 
 
+def l2_to_sm_roofline(workload, ms_per_step):
+    """Secondary roofline of the single-pass H.v: besides its own row every
+    amplitude pulls `hops` up-hop neighbours through L2 -> SM, hops = sum over bonds of the probability
+    that the two sites are occupied differently = nbonds * 2 n (L - n) / (L (L - 1)); the ceiling is
+    the gather-only rate measured with tools/microbench.cu (profiles/r1_microbench_4x4.txt)."""
+    from math import comb
+
+    num_sites, lattice, n_up, n_dn = WORKLOADS[workload]
+    nbonds = len(neighbors_of(lattice, num_sites))
+    hops = nbonds * 2.0 * n_up * (num_sites - n_up) / (num_sites * (num_sites - 1))
+    dim = comb(num_sites, n_up) * comb(num_sites, n_dn)
+    nbytes = (hops + 1.0) * 8.0 * dim
+    achieved = nbytes / (ms_per_step * 1e-3) / 1e9
+    peak = 8700.0
+    return {"bound": "l2_to_sm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "bytes_per_launch": nbytes, "up_hops_per_state": hops,
+            "peak_source": "measured gather-only kernel, profiles/r1_microbench_4x4.txt"}
+
+
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
@@ -377,6 +396,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if world == 1:
+            try:
+                line["roofline_l2_to_sm"] = l2_to_sm_roofline(args.workload, ms_per_step)
+            except Exception:  # explanatory extra, never in the way of the contract line
+                pass
         if lanczos is not None:
             line["lanczos_e0"] = lanczos
         if world == 1 and not args.no_cpu_baseline:
