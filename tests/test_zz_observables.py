@@ -57,6 +57,6 @@ def test_ground_state_correlations_heisenberg_chain(cm):
     gs = np.asarray(res.vector.cpu().numpy() if hasattr(res.vector, "cpu") else res.vector, dtype=np.float64)
     gs = gs / np.linalg.norm(gs)
     c = obs.spin_correlations(N, 0, gs, pos=0)
-    assert c[0] == 0.25 and c[1] < 0 < c[2] and c[3] < 0
+    assert abs(c[0] - 0.25) < 1e-14 and c[1] < 0 < c[2] and c[3] < 0
     zz = sum(obs.sz_correl(N, 0, gs, 1, pos=i) for i in range(N - 1))
     assert abs(2.0 * jz * zz - float(np.dot(gs * gs, h.diagonal()))) < 1e-12
