@@ -46,7 +46,7 @@ struct HubbardOp : cmpy_op_s {
   ClsTables cls2;            // the same sector with the engine-2 table set (chunked tasks)
   LongTables lng2;           // long rows, engine 2
   int cls_engine = 0;        // engine the default (variant 0) class-major launches use: 0 or 2
-  int cls2_threads = 1024;   // CTA size of the engine-2 launches (512 / 768 / 1024)
+  int cls2_threads = 1024;   // CTA size of the engine-2 launches (512 / 768 / 896 / 1024)
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
@@ -221,6 +221,9 @@ struct HubbardOp : cmpy_op_s {
       if (cls2_threads == 512) {
         if (!p.with_up) hub_cls_kernel<LZ, 512, 0, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
         else hub_cls_kernel<LZ, 512, 16, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
+      } else if (cls2_threads == 896) {
+        if (!p.with_up) hub_cls_kernel<LZ, 896, 0, false, false, 2><<<(int)g, 896, T.smem, st>>>(cp);
+        else hub_cls_kernel<LZ, 896, 10, false, false, 2><<<(int)g, 896, T.smem, st>>>(cp);
       } else if (cls2_threads == 768) {
         if (!p.with_up) hub_cls_kernel<LZ, 768, 0, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
         else hub_cls_kernel<LZ, 768, 12, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
@@ -312,6 +315,10 @@ struct HubbardOp : cmpy_op_s {
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 1024, 0, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 896, 10, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 896, 10, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 896, 0, false, false, 2>, smem_optin);
+      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 896, 0, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 12, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 768, 12, false, false, 2>, smem_optin);
       if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 0, false, false, 2>, smem_optin);
@@ -323,7 +330,7 @@ struct HubbardOp : cmpy_op_s {
       if (rc) return rc;
       if (const char* e = getenv("CMPY_CLS2_THREADS")) {
         const int t = atoi(e);
-        if (t == 512 || t == 768 || t == 1024) cls2_threads = t;
+        if (t == 512 || t == 768 || t == 896 || t == 1024) cls2_threads = t;
       }
       CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8, false, false, 2>, 1024, cls2.smem));
       if (nb < 1) cls2.release();

@@ -107,7 +107,7 @@ if __name__ == "__main__":
         ncu_launches()
         sys.exit(0)
     if mode == "threads":  # engine 2 with 512 / 768 / 1024-thread CTAs and 16..64 work pieces
-        for nt, npc in ((512, 16), (512, 32), (512, 48), (768, 24), (768, 48), (1024, 32)):
+        for nt, npc in ((512, 16), (512, 32), (768, 24), (896, 28), (896, 56), (1024, 32)):
             os.environ["CMPY_CLS2_THREADS"] = str(nt)
             os.environ["CMPY_CLS_PIECES"] = str(npc)
             run(f"c4_square4x4_t{nt}_p{npc}", 16, square(4, 4), 8, 8, [9], [5, 9])
