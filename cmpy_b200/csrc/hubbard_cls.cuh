@@ -154,7 +154,9 @@ CLS_HD int cls_min(int a, int b) { return a < b ? a : b; }
 // Engine 2 addresses shared memory through explicit byte addresses (32-bit shared-space addresses
 // on the device, so that "per-lane base + warp-uniform offset" is one LEA/IADD per access instead
 // of a re-derivation from the buffer base; plain pointers on the host).
-static std::vector<uintptr_t>* g_cls_trace = nullptr;   // host only (tests/emu): addresses of one lane's loads, in order
+#ifdef CMPY_EMU
+static std::vector<uintptr_t>* g_cls_trace = nullptr;   // tests/emu only: addresses of one lane's loads, in order
+#endif
 #ifdef __CUDA_ARCH__
 typedef uint32_t cls_addr;
 __device__ __forceinline__ cls_addr cls_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -171,7 +173,9 @@ __device__ __forceinline__ void cls_st(cls_addr a, double v) {
 typedef uintptr_t cls_addr;
 inline cls_addr cls_base(const void* p) { return (uintptr_t)p; }
 inline double cls_ld(cls_addr a) {
+#ifdef CMPY_EMU
   if (g_cls_trace) g_cls_trace->push_back(a);
+#endif
   return *reinterpret_cast<const double*>(a);
 }
 inline double cls_ld_y(cls_addr a) { return *reinterpret_cast<const double*>(a); }   // predicated load: not traced

@@ -9,6 +9,7 @@
 // evaluation of (D + T_dn) x on one row (ref: cmpy/operators.py:305-527).
 //
 // Built by the test itself:  nvcc -O1 -std=c++17 -shared -Xcompiler -fPIC cls_emu.cu
+#define CMPY_EMU 1   // enables the load-address trace hook of the host-side cls_ld
 #include "../../cmpy_b200/csrc/hubbard_cls.cuh"
 #include <cmath>
 
