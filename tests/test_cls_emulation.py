@@ -161,6 +161,9 @@ def test_engines_agree_and_use_fewer_tasks(emu, eng):
         # no piece is far above the mean in block x column units (the split balances the estimated
         # instruction count, in which a 3-block column costs less than three 1-block columns)
         assert info[6] * npc <= 2.0 * info[7] and info[8] * npc <= 2.0 * info[9], info
+        # shared-memory wavefronts of the engine-2 loads (x 1000): phase B is conflict-free, phase A
+        # within 30 % of conflict-free (the per-lane LH source segments are the only irregular accesses)
+        assert info[15] == 0 and info[13] <= info[14] + 1 and info[11] <= 1.3 * info[12] + 1, info
     ref = direct_row(L, n, square(4, 4), L, 4.0, 1.0, 0b1010110010100110, -16.0, x)
     assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
 
