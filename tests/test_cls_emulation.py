@@ -415,3 +415,63 @@ def test_weighted_elements_bit_exact(emu):
                 v += vals[k]
         ref[i] = v
     np.testing.assert_array_equal(out, ref)
+
+
+# ---------------------------------------------------------------------------------------
+# randomised lattices (hypothesis): arbitrary bond graphs, fillings and sign widths
+# ---------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def random_lattice(draw, max_sites=13):
+    L = draw(st.integers(4, max_sites))
+    n = draw(st.integers(1, L - 1))
+    pairs = [(a, b) for a in range(L) for b in range(a + 1, L)]
+    bonds = draw(st.lists(st.sampled_from(pairs), min_size=1, max_size=min(len(pairs), 14), unique=True))
+    width = draw(st.sampled_from([0, L]))
+    ups = draw(st.integers(0, (1 << L) - 1))
+    seed = draw(st.integers(0, 2 ** 16))
+    return L, n, sorted(bonds), width, ups, seed
+
+
+@settings(max_examples=40, deadline=None)
+@given(random_lattice())
+def test_random_lattices_class_major(emu, case):
+    L, n, bonds, width, ups, seed = case
+    x = np.random.default_rng(seed).standard_normal(len(orc.enumerate_states(L, n)))
+    ref = direct_row(L, n, bonds, width, 2.5, -0.9, ups, 0.7, x)
+    for eng in (0, 2):
+        rc, y, _ = run_emu(emu, L, n, bonds, width, 2.5, -0.9, ups, 0.7, eng, x)
+        if rc == 1:
+            continue   # odd row length, or more straddling bonds than engine 2 keeps in registers
+        assert rc == 0, (rc, case, eng)
+        assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (case, eng)
+
+
+@settings(max_examples=40, deadline=None)
+@given(random_lattice(), st.booleans())
+def test_random_lattices_segment_kernel(emu, case, uniform):
+    L, n, bonds, width, ups, seed = case
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(len(orc.enumerate_states(L, n)))
+    if uniform:
+        hop, u, eps = np.full(len(bonds), 1.1), np.full(L, 2.0), np.full(L, 0.4)
+    else:
+        hop, u, eps = rng.uniform(-1.5, 1.5, len(bonds)), rng.uniform(0.0, 4.0, L), rng.uniform(-1.0, 1.0, L)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    emu.emu_seg_row.restype = ctypes.c_int
+    emu.emu_seg_row.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, ctypes.c_int, dp, dp, dp,
+                                ctypes.c_int, ctypes.c_uint, ctypes.c_double, dp, dp]
+    s1 = np.ascontiguousarray([b[0] for b in bonds], dtype=np.int32)
+    s2 = np.ascontiguousarray([b[1] for b in bonds], dtype=np.int32)
+    hop, u, eps = (np.ascontiguousarray(a, dtype=np.float64) for a in (hop, u, eps))
+    y = np.empty_like(x)
+    rc = emu.emu_seg_row(L, n, len(bonds), s1.ctypes.data_as(ip), s2.ctypes.data_as(ip), width,
+                         hop.ctypes.data_as(dp), u.ctypes.data_as(dp), eps.ctypes.data_as(dp), int(uniform), ups, -0.2,
+                         x.ctypes.data_as(dp), y.ctypes.data_as(dp))
+    if rc == 1:
+        return
+    assert rc == 0, (rc, case)
+    ref = direct_row_general(L, n, bonds, width, hop, u, eps, ups, -0.2, x)
+    assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), case
