@@ -475,3 +475,32 @@ def test_random_lattices_segment_kernel(emu, case, uniform):
     assert rc == 0, (rc, case)
     ref = direct_row_general(L, n, bonds, width, hop, u, eps, ups, -0.2, x)
     assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), case
+
+
+@st.composite
+def random_long_lattice(draw):
+    L = draw(st.integers(17, 20))
+    n = draw(st.integers(1, 4))
+    pairs = [(a, b) for a in range(L) for b in range(a + 1, L)]
+    bonds = draw(st.lists(st.sampled_from(pairs), min_size=1, max_size=12, unique=True))
+    width = draw(st.sampled_from([0, L]))
+    ups = draw(st.integers(0, (1 << L) - 1))
+    seed = draw(st.integers(0, 2 ** 16))
+    return L, n, sorted(bonds), width, ups, seed
+
+
+@settings(max_examples=30, deadline=None)
+@given(random_long_lattice())
+def test_random_lattices_long_rows(emu, case):
+    """Random bond graphs on 17-20 sites: bonds inside the low 16 bits, inside the top bits and
+    straddling site 15 | 16 in every mixture."""
+    L, n, bonds, width, ups, seed = case
+    x = np.random.default_rng(seed).standard_normal(len(orc.enumerate_states(L, n)))
+    ref = direct_row(L, n, bonds, width, 3.0, 0.8, ups, -0.4, x)
+    for eng in (0, 2):
+        rc, y, cov = run_long(emu, L, n, bonds, width, 3.0, 0.8, ups, -0.4, eng, x)
+        if rc == 1:
+            continue
+        assert rc == 0, (rc, case, eng)
+        if cov.any():
+            assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (case, eng)
