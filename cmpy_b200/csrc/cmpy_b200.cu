@@ -472,13 +472,7 @@ API int cmpy_transpose_pull_acc_part(double* d_y_slab, int64_t nrows, int64_t nu
   if (rc) return rc;
   ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
   PeerPart pp;
-  pp.vstart[0] = 0;
-  for (int q = 0; q < world; ++q) {
-    const i64 n = pt.cb[q + 1] - pt.cb[q];
-    const i64 lo = pt.cb[q] + n * part / nparts, hi = pt.cb[q] + n * (part + 1) / nparts;
-    pp.lo[q] = lo;
-    pp.vstart[q + 1] = pp.vstart[q] + (hi - lo);
-  }
+  peer_part_fill(pp, pt, part, nparts);
   const i64 vtot = pp.vstart[world];
   if (nrows == 0 || vtot == 0) return CMPY_OK;
   const i64 ntiles = ((nrows + 31) / 32) * ((vtot + 31) / 32);

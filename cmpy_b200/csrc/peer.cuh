@@ -100,11 +100,22 @@ struct PeerPart {
   i64 vstart[PEER_MAX + 1];  // prefix sums of the part lengths
 };
 
-__device__ __forceinline__ i64 peer_part_column(const PeerTable& t, const PeerPart& pp, i64 v, int& q) {
+__host__ __device__ __forceinline__ i64 peer_part_column(const PeerTable& t, const PeerPart& pp, i64 v, int& q) {
   q = 0;
 #pragma unroll 1
   while (q + 1 < t.world && v >= pp.vstart[q + 1]) ++q;
   return pp.lo[q] + (v - pp.vstart[q]);
+}
+
+// part `part` of `nparts` of every owner's column range (host side of cmpy_transpose_pull_acc_part)
+static inline void peer_part_fill(PeerPart& pp, const PeerTable& pt, int part, int nparts) {
+  pp.vstart[0] = 0;
+  for (int q = 0; q < pt.world; ++q) {
+    const i64 n = pt.cb[q + 1] - pt.cb[q];
+    const i64 lo = pt.cb[q] + n * part / nparts, hi = pt.cb[q] + n * (part + 1) / nparts;
+    pp.lo[q] = lo;
+    pp.vstart[q + 1] = pp.vstart[q] + (hi - lo);
+  }
 }
 
 template <int PEER_TR>
