@@ -24,6 +24,18 @@ def test_header_symbols_exported():
     assert _lib.lib().cmpy_version() >= 100
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (plain pointers and sizes only)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                          os.path.join(ROOT, "include", "cmpy_b200.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_binomial_and_errors():
     assert _lib.binomial(20, 10) == 184756
     assert _lib.binomial(32, 16) == 601080390
