@@ -36,6 +36,24 @@ def test_header_is_plain_c():
     assert res.returncode == 0, res.stderr
 
 
+def test_c_example_compiles_and_links():
+    """examples/e0_from_c.c: a plain-C client of the ABI (no Python, no PyTorch) builds against the
+    header and links against the shared library."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        res = subprocess.run(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                              os.path.join(ROOT, "examples", "e0_from_c.c"), "-L", os.path.dirname(_lib.LIB_PATH),
+                              "-lcmpy_b200", "-L", cuda_lib, "-lcudart", "-lm", "-o", os.path.join(tmp, "e0")],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+
+
 def test_binomial_and_errors():
     assert _lib.binomial(20, 10) == 184756
     assert _lib.binomial(32, 16) == 601080390
