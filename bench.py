@@ -128,60 +128,162 @@ class ClockSampler:
 # reference arm: CPU port of the reference H.v on a bounded sample
 # ---------------------------------------------------------------------------------------
 
-def cpu_port_rate(workload, target_seconds, steps, warmup):
-    """Times oracle/hv_oracle.c (OpenMP, all host threads) on a contiguous sample of
-    up-rows of the workload; returns (matvec/s extrapolated to the full sector, info)."""
+def host_threads():
+    """Host threads the CPU arm uses: every core this process may run on.  Set explicitly --
+    torchrun exports OMP_NUM_THREADS=1 to its children, which must not shrink the baseline."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def build_port(workload):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import oracle_c
 
     num_sites, lattice, n_up, n_dn = WORKLOADS[workload]
     nb = neighbors_of(lattice, num_sites)
-    orc = oracle_c.hubbard_oracle(num_sites, n_up, n_dn, nb, PARAMS["inter"], -PARAMS["mu"],
-                                  PARAMS["hop"])
+    return oracle_c.hubbard_oracle(num_sites, n_up, n_dn, nb, PARAMS["inter"], -PARAMS["mu"], PARAMS["hop"])
+
+
+def cpu_port_rate(workload, target_seconds, steps, warmup, orc=None):
+    """Times oracle/hv_oracle.c (OpenMP over all host threads) on the workload.  The whole sector
+    is applied whenever `steps + warmup` full H.v fit `target_seconds`; otherwise a contiguous block
+    of up-rows from the middle of the sector, extrapolated linearly (said in `sample`)."""
+    import numpy as np
+
+    orc = build_port(workload) if orc is None else orc
     num_up = len(orc.up)
     x = np.random.default_rng(0).standard_normal(orc.size)
     x /= np.linalg.norm(x)
-    cores = oracle_c.max_threads()
-    # calibrate the sample size on a few rows (spread over the sector so gathers are typical)
-    probe = min(num_up, max(cores * 2, 16))
+    cores = host_threads()
+    probe = min(num_up, max(cores * 4, 64))
     row0 = (num_up - probe) // 2
+    orc.matvec_rows(x, row0, probe, nthreads=cores)          # first touch / thread pool start
     t0 = time.perf_counter()
-    orc.matvec_rows(x, row0, probe)
-    t_probe = time.perf_counter() - t0
-    per_row = t_probe / probe
+    orc.matvec_rows(x, row0, probe, nthreads=cores)
+    per_row = (time.perf_counter() - t0) / probe
     total_steps = max(1, steps + warmup)
     nrows = int(min(num_up, max(probe, target_seconds / total_steps / max(per_row, 1e-9))))
     row0 = (num_up - nrows) // 2
     for _ in range(warmup):
-        orc.matvec_rows(x, row0, nrows)
+        orc.matvec_rows(x, row0, nrows, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.matvec_rows(x, row0, nrows)
+        orc.matvec_rows(x, row0, nrows, nthreads=cores)
     dt = (time.perf_counter() - t0) / steps
     full = dt * num_up / nrows
+    what = "the whole sector" if nrows == num_up else "middle of the sector, extrapolated linearly"
     info = {"cores": cores, "kind": "port",
             "sample": f"{nrows} of {num_up} up-rows ({nrows * len(orc.dn)} of {orc.size} states) per "
-                      f"step, middle of the sector, extrapolated linearly; oracle/hv_oracle.c OpenMP"}
+                      f"step, {what}; oracle/hv_oracle.c, OpenMP with {cores} threads set explicitly"}
     return 1.0 / full, dt * 1e3, info
+
+
+def cpu_port_lanczos(workload, orc=None, budget_s=240.0):
+    """Second half of the metric on the CPU arm: the reference's ground-state call
+    `sla.eigsh(hamop, k=1, which="SA")` (cmpy/exactdiag.py:37) with the C port as the operator's
+    mat-vec, tol 1e-10.  Skipped (with the reason) when the estimate exceeds `budget_s`."""
+    import numpy as np
+    import scipy.sparse.linalg as sla
+
+    orc = build_port(workload) if orc is None else orc
+    cores = host_threads()
+    n = orc.size
+    x = np.random.default_rng(0).standard_normal(n)
+    x /= np.linalg.norm(x)
+    t0 = time.perf_counter()
+    orc.matvec(x, nthreads=cores)
+    t_mv = time.perf_counter() - t0
+    ncv = 12
+    est = 160 * (t_mv + 4.0 * ncv * 8.0 * n / 20e9)   # ~160 mat-vecs + BLAS-2 re-orthogonalisation
+    if est > budget_s:
+        return {"skipped": f"estimated {est:.0f} s > {budget_s:.0f} s budget", "matvec_s": t_mv, "cores": cores}
+    count = [0]
+
+    def mv(v):
+        count[0] += 1
+        return orc.matvec(np.ascontiguousarray(v, dtype=np.float64).reshape(-1), nthreads=cores)
+
+    op = sla.LinearOperator((n, n), matvec=mv, dtype=np.float64)
+    t0 = time.perf_counter()
+    ev = sla.eigsh(op, k=1, which="SA", tol=1e-10, ncv=ncv, v0=x, return_eigenvectors=False)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "e0": float(ev[0]), "matvecs": count[0], "tol": 1e-10, "ncv": ncv, "cores": cores,
+            "solver": "scipy.sparse.linalg.eigsh(k=1, which='SA') over the C port (cmpy/exactdiag.py:37)"}
+
+
+def cpu_scipy_path(max_sites=12):
+    """BASELINE.md section 3 baseline B -- the reference's scipy CSR path (`hubbard_hamiltonian`,
+    cmpy/models/hubbard.py:25-34: COO triplets -> csr_matrix -> A @ x, eigsh(A, k=1, which='SA')) --
+    restated with oracle/oracle_np.py (kind "port": /root/reference does not exist on the GPU box),
+    open chains at half filling, single-threaded SpMV as in the reference."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    import oracle_np as orc
+
+    out = []
+    for L in (8, 10, 12):
+        if L > max_sites:
+            break
+        n = L // 2
+        st = orc.enumerate_states(L, n)
+        t0 = time.perf_counter()
+        r, c, v = orc.hubbard_triplets(st, st, L, orc.chain_neighbors(L), PARAMS["inter"], -PARAMS["mu"],
+                                       PARAMS["hop"])
+        dim = len(st) ** 2
+        a = sp.csr_matrix((v, (r, c)), shape=(dim, dim))
+        t_build = time.perf_counter() - t0
+        x = np.random.default_rng(0).standard_normal(dim)
+        reps = max(3, int(2e7 / max(a.nnz, 1)))
+        a @ x
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            a @ x
+        t_mv = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        ev = sla.eigsh(a, k=1, which="SA", tol=1e-10, return_eigenvectors=False)
+        t_e0 = time.perf_counter() - t0
+        out.append({"config": f"hubbard_chain_L{L}_half_filling", "dim": dim, "nnz": int(a.nnz),
+                    "build_s": t_build, "matvec_per_s": 1.0 / t_mv, "eigsh_e0_s": t_e0, "e0": float(ev[0])})
+    return out
+
+
+def reference_verbatim_record():
+    """BASELINE.md section 3 baseline A (the unmodified reference: hamilton_operator +
+    HamiltonOperator.matvec + sla.eigsh) cannot run on the GPU box; the numbers measured in the
+    dev container by tools/reference_cpu_baseline.py are committed and quoted here."""
+    path = os.path.join(ROOT, "profiles", "r2_reference_cpu_baseline.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, ms_sample, info = cpu_port_rate(args.workload, 60.0, args.steps, args.warmup)
-    num_sites, lattice, n_up, n_dn = WORKLOADS[args.workload]
+    orc = build_port(args.workload)
+    rate, ms_sample, info = cpu_port_rate(args.workload, 60.0, args.steps, args.warmup, orc)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(args.workload, 1),
+        "config": workload_config(args.workload, args.gpus),
         "cpu_baseline": dict(value=rate, unit=UNIT, **info),
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_ms_per_step": ms_sample,
     }
+    if not args.no_lanczos:
+        try:
+            line["lanczos_e0"] = cpu_port_lanczos(args.workload, orc)
+        except Exception as exc:  # never in the way of the contract line
+            line["lanczos_e0"] = {"skipped": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
@@ -198,7 +300,6 @@ def workload_config(workload, n_gpus):
         "bytes_per_step_algorithmic": 16 * dim,
         "l2_policy": ("inputs larger than L2 (8*dim bytes per vector), no flush"
                       if 8 * dim > 200e6 else "L2 flushed between timed iterations"),
-        "parallelism": "single GPU" if n_gpus == 1 else f"up-string sharded x{n_gpus}, NCCL all-to-all",
     }
 
 
@@ -224,6 +325,42 @@ def l2_to_sm_roofline(workload, ms_per_step):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+
+def parity_check(workload, hamop, x, y, world, dev):
+    """Outside the timed region: rows of y = H x of the benchmarked operator against the C oracle
+    (oracle/hv_oracle.c).  N = 1: 32-row blocks at the start, middle and end of the sector; N > 1:
+    the same for rank 0's slab (x of the other ranks is regenerated from their seeds)."""
+    import numpy as np
+    import torch
+
+    orc = build_port(workload)
+    nd = len(orc.dn)
+    if world == 1:
+        hamop.apply(x, out=y)
+        torch.cuda.synchronize()
+        xf = x.cpu().numpy()
+        r_lo, r_hi = 0, len(orc.up)
+    else:
+        hamop.apply_local(x, out=y)
+        torch.cuda.synchronize()
+        parts = []
+        for r in range(world):
+            a, b = hamop.plan.rows(r)
+            g = torch.Generator(device=dev); g.manual_seed(r)
+            parts.append(torch.randn((b - a) * nd, dtype=torch.float64, device=dev, generator=g).cpu().numpy())
+        xf = np.concatenate(parts)
+        r_lo, r_hi = hamop.plan.rows(0)
+    nblk = min(32, r_hi - r_lo)
+    worst, scale = 0.0, 0.0
+    rows = sorted({r_lo, (r_lo + r_hi - nblk) // 2, r_hi - nblk})
+    for r0 in rows:
+        ref = orc.matvec_rows(xf, r0, nblk, nthreads=host_threads())
+        got = y[(r0 - r_lo) * nd:(r0 - r_lo + nblk) * nd].cpu().numpy()
+        scale = max(scale, float(np.abs(ref).max()))
+        worst = max(worst, float(np.abs(got - ref).max()))
+    return {"max_rel_err": worst / max(scale, 1e-300), "rows_checked": [int(r) for r in rows],
+            "rows_per_block": int(nblk), "oracle": "oracle/hv_oracle.c", "tolerance": 1e-12}
+
 
 def run_ours(args):
     import numpy as np
@@ -326,9 +463,10 @@ def run_ours(args):
     xh.copy_(x.cpu())
     h2d = d2h = 8 * local_elems * world
 
+    yh_out = torch.empty(local_elems, dtype=torch.float64).pin_memory()
+
     def e2e_step():
-        yh = hamop.matvec(xh)  # CPU (pinned) tensor in -> pinned CPU tensor out
-        return yh
+        return hamop.matvec(xh, out=yh_out)  # pinned CPU tensor in -> pinned CPU tensor out
 
     for _ in range(2):
         e2e_step()
@@ -355,6 +493,32 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_value = e2e_steps / (time.perf_counter() - t0)
 
+    # the call scipy makes (eigsh / expm_multiply hand `_matvec` a pageable numpy vector)
+    e2e_numpy = None
+    if world == 1:
+        xn = xh.numpy().copy()
+        hamop.matvec(xn)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            hamop.matvec(xn)
+        e2e_numpy = 3 / (time.perf_counter() - t0)
+        del xn
+
+    # ---- parity of THIS configuration against the C oracle, outside the timed region ---------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = parity_check(args.workload, hamop, x, y, world, dev)
+        except Exception as exc:
+            parity = {"error": repr(exc)}
+    phases = None
+    if world > 1 and getattr(hamop, "exchange", "") == "peer":
+        try:
+            phases = hamop.profile_phases(x, y, reps=5)
+        except Exception as exc:
+            phases = {"error": repr(exc)}
+        step()
+
     # ---- Lanczos E0 to 1e-10 (second half of the BASELINE metric), single GPU only --------
     lanczos = None
     if world == 1 and not args.no_lanczos:
@@ -373,7 +537,7 @@ def run_ours(args):
         achieved = 16.0 * dim / world / (ms_per_step * 1e-3) / 1e9  # per GPU
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "hv_traffic.json")
-        if os.path.exists(tpath):
+        if world == 1 and os.path.exists(tpath):   # ncu figure of the single-GPU kernel only
             try:
                 traffic = json.load(open(tpath)).get(args.workload)
             except Exception:
@@ -386,7 +550,8 @@ def run_ours(args):
             "achieved_hbm_gbs_algorithmic": achieved * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "hub_seg_kernel" if world == 1 else "sharded step (per GPU)",
+                         "kernel": (getattr(hamop, "kernel_name", lambda: "hubbard H.v kernel")()
+                                    if world == 1 else "sharded step (per GPU): dn pass, push, up pass, pull"),
                          "algorithmic_bytes_per_launch": 16 * dim // world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -395,7 +560,27 @@ def run_ours(args):
                     "single_call_value": e2e_single},
             "gpu_launches": launches,
             "clocks": clocks,
+            "parallelism": ("single GPU" if world == 1 else
+                            f"up-string sharded x{world}; " + (
+                                "peer-memory push/pull transposes over NVLink (symmetric memory), NCCL for "
+                                "barriers / scalar all-reduces only" if getattr(hamop, "exchange", "") == "peer"
+                                else "NCCL all-to-all transposes")),
         }
+        if parity is not None:
+            line["parity_max_rel_err"] = parity.get("max_rel_err")
+            line["parity"] = parity
+        if e2e_numpy is not None:
+            line["e2e"]["numpy_call_value"] = e2e_numpy
+            line["e2e"]["numpy_call_api"] = "HamiltonOperator.matvec(np.ndarray) -- the call sla.eigsh makes"
+        if world > 1:
+            out_bytes = hamop.plan.bytes_out_per_hv()
+            nv = out_bytes / (ms_per_step * 1e-3) / 1e9
+            line["roofline_nvlink"] = {"bound": "nvlink", "bytes_out_per_gpu_per_step": out_bytes,
+                                       "achieved": nv, "peak": 900.0, "unit": "GB/s", "frac": nv / 900.0,
+                                       "frac_of_measured_peer_copy_770": nv / 770.0,
+                                       "note": "bytes leaving rank 0 per H.v (two transposes) / whole step time"}
+            if phases is not None:
+                line["phases_ms_serialised"] = phases
         if world == 1:
             try:
                 line["roofline_l2_to_sm"] = l2_to_sm_roofline(args.workload, ms_per_step)
@@ -406,6 +591,15 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             rate, ms_sample, info = cpu_port_rate(args.workload, 12.0, 2, 1)
             line["cpu_baseline"] = dict(value=rate, unit=UNIT, **info)
+            extra = {}
+            try:
+                extra["scipy_csr_path_port"] = cpu_scipy_path()
+            except Exception as exc:
+                extra["scipy_csr_path_port"] = {"error": repr(exc)}
+            rec = reference_verbatim_record()
+            if rec is not None:
+                extra["reference_verbatim_dev_container"] = rec
+            line["cpu_baseline"]["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -422,6 +616,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-lanczos", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

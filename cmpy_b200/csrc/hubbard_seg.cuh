@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT, 1) hub_seg_kernel(SegParams sp) {
     uint4* dst = reinterpret_cast<uint4*>(tab);
     for (int k = tid; k < L.bytes / 16; k += nt) dst[k] = src[k];
     for (int k = tid; k < ndi; k += nt) s_dn[k] = p.dn_states[k];
-    if (tid < ELL_MAX_BONDS) s_hop[tid] = p.hop[tid];
+    for (int k = tid; k < ELL_MAX_BONDS; k += nt) s_hop[k] = p.hop[k];   // CTAs may have only 32 threads
     if (tid < 32) s_u[tid] = tid < p.num_sites ? p.u[tid] : 0.0;
   }
   int j; double s1, s2; bool has_prev;
@@ -216,13 +216,13 @@ __global__ void __launch_bounds__(NT, 1) hub_seg_kernel(SegParams sp) {
       for (int d = tid; d < ndi; d += nt) xs[d] = xr[d];
     }
     const int cu = p.with_up ? (int)p.cnt_up[u] : 0;
-    if (tid < cu) {
-      const uint32_t e = p.ell_up[(i64)tid * nu + u];
+    for (int k = tid; k < cu; k += nt) {   // strided: cu can exceed a 32-thread CTA (> 32 bonds)
+      const uint32_t e = p.ell_up[(i64)k * nu + u];
       UpEnt ue;
       ue.off = ((i64)(e & ELL_TGT_MASK) - u) * nd;  // relative to the current row
       const double hv = UNI ? p.hop0 : s_hop[(e >> ELL_TGT_BITS) & 63u];
       ue.coef = (e >> 31) ? -hv : hv;
-      s_up[tid] = ue;
+      s_up[k] = ue;
     }
     __syncthreads();
     const uint32_t ups = p.up_states[u];

@@ -383,19 +383,24 @@ class ShardedHubbardOperator:
             off += send_counts[q]
         return out
 
-    def matvec(self, x_local):
+    def matvec(self, x_local, out=None):
         """Public call on the local slab: CUDA tensor in -> CUDA tensor out; CPU (pinned)
-        tensor in -> pinned CPU tensor out (H2D + H.v + D2H)."""
+        tensor in -> CPU tensor out (H2D + H.v + D2H).  The host result is a fresh tensor unless
+        ``out`` (CPU float64, pinned for full speed) is given."""
         torch = _lib.require_cuda()
         if x_local.is_cuda:
             return self.apply_local(x_local)
         dev = x_local.to(_lib.device(), non_blocking=True)
         y = self.apply_local(dev)
+        if out is not None:
+            out.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
         if self._pinned_out is None:
             self._pinned_out = torch.empty(self.local_size, dtype=torch.float64).pin_memory()
         self._pinned_out.copy_(y, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self._pinned_out
+        return self._pinned_out.clone()
 
 
 def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, seed=0, callback=None,

@@ -268,20 +268,42 @@ class _DeviceOperatorMixin:
                                             _lib.stream_ptr()), "cmpy_hv_apply")
         return out
 
-    def _apply_any(self, x):
-        """numpy in -> numpy out (host round trip); CUDA tensor in -> CUDA tensor out."""
+    def _host_staging(self, n):
+        """Two cached pinned host buffers of the operator's size (input and result staging)."""
+        torch = _lib.require_cuda()
+        st = getattr(self, "_pinned_io", None)
+        if st is None or st[0].numel() != n:
+            st = (torch.empty(n, dtype=torch.float64).pin_memory(),
+                  torch.empty(n, dtype=torch.float64).pin_memory())
+            self._pinned_io = st
+        return st
+
+    def _apply_any(self, x, out=None):
+        """numpy in -> numpy out (host round trip); CUDA tensor in -> CUDA tensor out.
+
+        Host data goes through two cached pinned staging buffers (multi-threaded host copy into
+        the pinned input, asynchronous H2D, H.v, asynchronous D2H into the pinned result).  The
+        returned host array / tensor is FRESH unless the caller passes ``out`` (a CPU float64
+        tensor, pinned for full speed) -- the reference's ``_matvec`` never aliases its results
+        (cmpy/operators.py:626-630)."""
         torch = _lib.require_cuda()
         if isinstance(x, torch.Tensor) and not x.is_cuda and not x.is_complex():
-            # host tensor (pinned memory = fast path): H2D, H.v, D2H into a pinned buffer
-            dev = x.to(device=_lib.device(), dtype=torch.float64, non_blocking=True)
+            n = x.numel()
+            src = x.contiguous().view(-1)
+            if src.dtype != torch.float64 or not src.is_pinned():
+                pin_in, _ = self._host_staging(n)
+                pin_in.copy_(src)
+                src = pin_in
+            dev = src.to(device=_lib.device(), non_blocking=True)
             y = self.apply(dev)
-            out = getattr(self, "_pinned_out", None)
-            if out is None or out.numel() != y.numel():
-                out = torch.empty(y.numel(), dtype=torch.float64).pin_memory()
-                self._pinned_out = out
-            out.copy_(y, non_blocking=True)
+            if out is not None:
+                out.view(-1).copy_(y, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return out.view(x.shape)
+            _, pin_out = self._host_staging(n)
+            pin_out.copy_(y, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return out.view(x.shape)
+            return pin_out.clone().view(x.shape)
         if isinstance(x, torch.Tensor):
             if x.is_complex():
                 xr = torch.view_as_real(x.contiguous().view(-1))
@@ -295,14 +317,22 @@ class _DeviceOperatorMixin:
             re = self._apply_any(np.ascontiguousarray(flat.real))
             im = self._apply_any(np.ascontiguousarray(flat.imag))
             return (re + 1j * im).astype(np.result_type(flat.dtype, np.complex128)).reshape(shape)
-        dev = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64)).to(_lib.device())
-        y = self.apply(dev).cpu().numpy()
-        return y.reshape(shape)
+        # what scipy (eigsh, expm_multiply) hands over: a pageable numpy vector
+        host = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64))
+        res = torch.empty(host.numel(), dtype=torch.float64)
+        pin_in, pin_out = self._host_staging(host.numel())
+        pin_in.copy_(host)
+        dev = pin_in.to(device=_lib.device(), non_blocking=True)
+        y = self.apply(dev)
+        pin_out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        res.copy_(pin_out)
+        return res.numpy().reshape(shape)
 
-    def matvec(self, x):
+    def matvec(self, x, out=None):
         torch = _lib.torch_mod()
         if isinstance(x, torch.Tensor):
-            return self._apply_any(x)
+            return self._apply_any(x, out=out)
         return super().matvec(x)
 
     def matvec_batch(self, xs, outs=None):

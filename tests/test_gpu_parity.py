@@ -308,6 +308,38 @@ def test_lanczos_fused_class_major_variants(cm):
     h.set_variant(0)
 
 
+def test_hv_more_than_32_bonds_tiny_dn_sectors(cm):
+    """A lattice with 40 bonds (4 x 5 torus, 20 sites) in sectors whose dn list has <= 64 strings:
+    the segment kernel then runs 32-thread CTAs and must still fill all 40 bond slots of its
+    per-row tables (round-1 advisor finding, hubbard_seg.cuh)."""
+    from cmpy_b200.models import HubbardModel
+
+    nx, ny = 4, 5
+    nb = []
+    for r in range(ny):
+        for c in range(nx):
+            i = nx * r + c
+            for j in (nx * r + (c + 1) % nx, nx * ((r + 1) % ny) + c):
+                nb.append([min(i, j), max(i, j)])
+    assert len(nb) == 40
+    L = nx * ny
+    for kw in (dict(inter=4.0, mu=2.0, hop=1.0), dict(inter=2.0, mu=0.3, hop=-0.8)):
+        model = HubbardModel(L, nb, **kw)
+        for nu, nd in [(2, 0), (2, 1), (3, 1), (2, 19), (1, 20), (10, 1)]:
+            up, dn = orc.enumerate_states(L, nu), orc.enumerate_states(L, nd)
+            h = model.hamilton_operator(nu, nd)
+            x = np.random.default_rng(3).standard_normal(h.shape[0])
+            ref = orc.hubbard_matvec_free(up, dn, nb, kw["inter"], -kw["mu"], kw["hop"], x, width=L)
+            for variant in (0, 1, 3):
+                try:
+                    h.set_variant(variant)
+                    y = h.matvec(x)
+                except RuntimeError as exc:
+                    assert "variant" in str(exc), exc
+                    continue
+                assert relerr(y, ref) < HV_RTOL, (nu, nd, variant)
+
+
 def test_hv_siam_vs_oracle(cm):
     from cmpy_b200.models import SingleImpurityAndersonModel
 
@@ -362,12 +394,59 @@ def test_hv_torch_zero_copy_and_properties_c4(cm):
         hx1 = h.matvec(x)
         assert float((hx1 - hx).abs().max()) < 1e-12 * float(hx.abs().max()), variant
     h.set_variant(0)
-    # spot rows against the oracle: restrict x to one up-row neighbourhood is not possible
-    # matrix-free, so compare the diagonal instead
     d = h.diagonal()
     up = orc.enumerate_states(16, 8)
     e = -2.0 * 16 + 4.0 * np.array([int(up[5] & s).bit_count() for s in up[:100]])
     assert_allclose(d[5 * 12870: 5 * 12870 + 100], e, atol=1e-12)
+
+
+def _c4_oracle():
+    import oracle_c
+
+    return oracle_c.hubbard_oracle(16, 8, 8, orc.square_neighbors(4, 4), 4.0, -2.0, 1.0)
+
+
+def test_hv_c4_full_vector_vs_oracle(cm):
+    """The benchmarked configuration itself (C4, dim 165 636 900, default kernel selection) against
+    the C oracle (oracle/hv_oracle.c, pinned to the reference fixtures by tests/test_oracle_c.py):
+    the WHOLE result vector, 1e-12 relative; then the fused Lanczos instantiation of the same kernel
+    through its first two coefficients (alpha_0 = <v|H|v>, beta_1 = |Hv - alpha_0 v|) computed from the
+    oracle's H.v.  ref: cmpy/operators.py:463-527, 626-630."""
+    import torch
+    from cmpy_b200.exactdiag import lanczos_run
+    from cmpy_b200.models import HubbardModel
+
+    oc = _c4_oracle()
+    model = HubbardModel(16, orc.square_neighbors(4, 4), inter=4.0, mu=2.0, hop=1.0)
+    h = model.hamilton_operator(8, 8)
+    n = h.shape[0]
+    assert n == oc.size == 165636900
+    x = np.random.default_rng(7).standard_normal(n)
+    x /= np.linalg.norm(x)
+    ref = oc.matvec(x)
+    scale = np.abs(ref).max()
+    xd = torch.from_numpy(x).cuda()
+    got = h.matvec(xd).cpu().numpy()
+    assert np.abs(got - ref).max() / scale < HV_RTOL
+    # sample rows of every explicit kernel variant that supports this sector
+    rows = [0, 6419, 12838]
+    for variant in (1, 4, 5, 9):
+        h.set_variant(variant)
+        yv = h.matvec(xd)
+        for r0 in rows:
+            sl = slice(r0 * 12870, (r0 + 32) * 12870)
+            assert np.abs(yv[sl].cpu().numpy() - ref[sl]).max() / scale < HV_RTOL, (variant, r0)
+        del yv
+    h.set_variant(0)
+    # fused Lanczos epilogue (the LZ instantiation): two iterations, coefficients from the oracle
+    a0 = float(x @ ref)
+    r1 = ref - a0 * x
+    b1 = float(np.linalg.norm(r1))
+    res = lanczos_run(h, xd, maxit=2, tol=0.0, check_every=2)
+    assert abs(res.alpha[0] - a0) < 1e-11 * max(1.0, abs(a0))
+    assert abs(res.beta[1] - b1) < 1e-11 * max(1.0, abs(b1))
+    a1 = float(r1 @ oc.matvec(r1)) / (b1 * b1)
+    assert abs(res.alpha[1] - a1) < 1e-10 * max(1.0, abs(a1))
 
 
 # ---------------------------------------------------------------------------------------

@@ -46,22 +46,3 @@ def test_partial_pull_with_virtual_ranks(nparts):
         n = cb[q + 1] - cb[q]
         expect[cb[q] + n * 0 // nparts: cb[q] + n * 1 // nparts] = True
     assert (touched == expect).all()
-
-
-def test_c_example_runs():
-    """examples/e0_from_c.c on the GPU: E0 of the 8-site chain from a plain-C client of the ABI."""
-    import subprocess
-    import tempfile
-
-    from cmpy_b200 import _lib
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    with tempfile.TemporaryDirectory() as tmp:
-        exe = os.path.join(tmp, "e0")
-        subprocess.run(["gcc", "-O1", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
-                        os.path.join(root, "examples", "e0_from_c.c"), "-L", os.path.dirname(_lib.LIB_PATH),
-                        "-lcmpy_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm",
-                        "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-o", exe], check=True)
-        res = subprocess.run([exe], capture_output=True, text=True)
-        assert res.returncode == 0, res.stdout + res.stderr
-        assert "E0 = -20.2358069991" in res.stdout
