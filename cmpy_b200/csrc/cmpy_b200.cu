@@ -175,6 +175,8 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
   if (!rc && fixed_popcount)
     rc = op->configure_cls(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (!rc && fixed_popcount)
+    rc = op->configure_eng(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
+  if (!rc && fixed_popcount)
     rc = op->configure_long(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (rc) { delete op; return rc; }
   {  // engine of the default class-major launches (0 until engine 2 is measured on the target box)
@@ -264,7 +266,7 @@ API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_
 }
 
 API int cmpy_hv_set_variant(cmpy_op_t op, int variant) {
-  ARG_CHECK(op && variant >= 0 && variant <= 10, "bad variant");
+  ARG_CHECK(op && variant >= 0 && variant <= 11, "bad variant");
   op->variant = variant;
   return CMPY_OK;
 }

@@ -5,6 +5,7 @@
 #include "hubbard.cuh"
 #include "hubbard_seg.cuh"
 #include "hubbard_cls.cuh"
+#include "hubbard_eng.cuh"
 
 // ---------------------------------------------------------------------------------
 struct SpeciesTables {
@@ -25,6 +26,19 @@ __global__ void narrow_states_kernel(const i64* __restrict__ in, i64 n, uint32_t
   for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
     out[i] = (uint32_t)in[i];
 }
+
+// device side of the generation-3 row engine: the constant-bank tables travel as a kernel
+// parameter, only the per-lane tables live in global memory
+struct EngTables {
+  EngHost H;
+  uint16_t* d_dh_cm = nullptr;
+  uint32_t* d_lh_lane = nullptr;
+  bool ok = false;
+  void release() {
+    cudaFree(d_dh_cm); cudaFree(d_lh_lane);
+    d_dh_cm = nullptr; d_lh_lane = nullptr; ok = false;
+  }
+};
 
 struct HubbardOp : cmpy_op_s {
   int num_sites = 0, nbonds = 0, sign_width = 0;
@@ -50,9 +64,12 @@ struct HubbardOp : cmpy_op_s {
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
+  EngTables eng;             // generation-3 row engine (constant-bank hop lists)
+  bool eng_full = false;     // variant 0 uses the engine for the full H.v too (up hops as row gathers)
 
   ~HubbardOp() override {
     up.release(); dn.release(); seg.release(); cls.release(); lng.release(); cls2.release(); lng2.release();
+    eng.release();
     cudaFree(d_hop); cudaFree(d_u);
   }
 
@@ -122,6 +139,10 @@ struct HubbardOp : cmpy_op_s {
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant (engine 2) not available for this call");
     if (use_variant == 9 && !(cls2.ok && UNI && aligned16))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant (engine 2) not available for this call");
+    if (use_variant == 11 && !(eng.ok && UNI))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row-engine variant not available for this sector");
+    if (use_variant == 11 || (use_variant == 0 && eng.ok && UNI && (!p.with_up || eng_full)))
+      return launch_eng<LZ>(p, st);
     if (use_variant == 10) return launch_long(p, st, lng2, 2);
     if (use_variant == 8 || (use_variant == 0 && lng.ok && UNI && aligned16 && !p.with_up && !LZ &&
                              (p.num_dn % 2 == 0))) {
@@ -204,6 +225,41 @@ struct HubbardOp : cmpy_op_s {
       else hub_seg_kernel<false, LZ, false, 512><<<(int)g, seg_threads, smem, st>>>(sp);
     }
     KERNEL_CHECK();
+    return CMPY_OK;
+  }
+
+  template <bool LZ>
+  int launch_eng(HubParams& p, cudaStream_t st) {
+    EngArgs A;
+    A.hp = p; A.ln.dh_cm = eng.d_dh_cm; A.ln.lh_lane = eng.d_lh_lane; A.e_dn_const = eng.H.e_dn_const;
+    i64 g = sm_count;
+    if (grid_limit > 0 && g > grid_limit) g = grid_limit;
+    if (g > p.nrows) g = p.nrows;
+    if (p.with_up) hub_eng_kernel<LZ, true, 1024><<<(int)g, 1024, eng.H.smem, st>>>(eng.H.C, A);
+    else hub_eng_kernel<LZ, false, 1024><<<(int)g, 1024, eng.H.smem, st>>>(eng.H.C, A);
+    KERNEL_CHECK();
+    return CMPY_OK;
+  }
+
+  // Generation-3 row engine: uniform hop / U / eps, hop != 0, complete dn sector of <= 16 sites.
+  int configure_eng(int n_dn, const int* s1, const int* s2, const double* eps) {
+    if (!(uniform && eps_uniform) || hop0 == 0.0 || dn.num < 64) return CMPY_OK;
+    int rc = build_eng_host(eng.H, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, 32, false);
+    if (rc || !eng.H.ok) return rc;
+    rc = raise_smem_limit(hub_eng_kernel<false, false, 1024>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, false, 1024>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<false, true, 1024>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, true, 1024>, smem_optin);
+    if (rc) return rc;
+    int nb = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_eng_kernel<true, true, 1024>, 1024, eng.H.smem));
+    if (nb < 1) return CMPY_OK;
+    CU_CHECK(cudaMalloc(&eng.d_dh_cm, sizeof(uint16_t) * eng.H.dh_cm.size()));
+    CU_CHECK(cudaMalloc(&eng.d_lh_lane, sizeof(uint32_t) * eng.H.lh_lane.size()));
+    CU_CHECK(cudaMemcpy(eng.d_dh_cm, eng.H.dh_cm.data(), sizeof(uint16_t) * eng.H.dh_cm.size(), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMemcpy(eng.d_lh_lane, eng.H.lh_lane.data(), sizeof(uint32_t) * eng.H.lh_lane.size(), cudaMemcpyHostToDevice));
+    eng.ok = true;
+    if (const char* e = getenv("CMPY_ENG_FULL")) eng_full = atoi(e) != 0;
     return CMPY_OK;
   }
 

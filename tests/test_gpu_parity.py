@@ -235,7 +235,7 @@ def test_hv_l8_golden_both_kernels(cm, golden):
     model = HubbardModel(8, chain(8), inter=4.0, mu=2.0, hop=1.0)
     h = model.hamilton_operator(4, 4)
     x = np.cos(0.37 * np.arange(4900))
-    for variant in (1, 2, 3, 5, 6, 7):
+    for variant in (1, 2, 3, 5, 6, 7, 11):
         h.set_variant(variant)
         y = h.matvec(x)
         assert relerr(y, golden["hub_chain8_44_hv"]) < HV_RTOL
@@ -272,7 +272,7 @@ def test_hv_vs_oracle(cm, L, nu, nd, nbfn, kw):
     ref = orc.hubbard_matvec_free(up, dn, nb, kw.get("inter", 0.0), kw.get("eps", 0.0) - kw.get("mu", 0.0),
                                   kw.get("hop", 1.0), x, width=L)
     ran = []
-    for variant in (1, 2, 3, 5, 6, 7):
+    for variant in (1, 2, 3, 5, 6, 7, 11):
         try:
             h.set_variant(variant)
             y = h.matvec(x)
@@ -301,7 +301,7 @@ def test_lanczos_fused_class_major_variants(cm):
     import scipy.sparse as sp
     a = sp.csr_matrix((v, (r, c)), shape=(h.shape[0],) * 2)
     e_ref = sla.eigsh(a, k=1, which="SA", tol=0)[0][0]
-    for variant in (5, 6, 7, 3):
+    for variant in (5, 6, 7, 3, 11):
         h.set_variant(variant)
         res = lanczos_run(h, None, maxit=400, tol=1e-12, resid_tol=1e-9)
         assert abs(res.e0 - e_ref) < 1e-10, (variant, res.e0, e_ref)
@@ -430,7 +430,7 @@ def test_hv_c4_full_vector_vs_oracle(cm):
     assert np.abs(got - ref).max() / scale < HV_RTOL
     # sample rows of every explicit kernel variant that supports this sector
     rows = [0, 6419, 12838]
-    for variant in (1, 4, 5, 9):
+    for variant in (1, 4, 5, 9, 11):
         h.set_variant(variant)
         yv = h.matvec(xd)
         for r0 in rows:
