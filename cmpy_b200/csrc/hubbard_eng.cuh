@@ -32,8 +32,8 @@
 
 #define ENG_MAX_CLS 9        // m <= 8 low bits -> classes 0..8
 #define ENG_MAX_LH 4         // LH bonds whose per-lane state phase A keeps in registers
-#define ENG_MAX_TASKS 160
-#define ENG_MAX_ENT 2304     // u16 entries per hop-list table
+#define ENG_MAX_TASKS 96
+#define ENG_MAX_ENT 1664     // u8 entries per hop-list table
 #define ENG_MAX_Q 256        // dl values (2^m)
 #define ENG_MAX_SEG 256      // dh values with a non-empty class
 #define ENG_ZREG 96          // zeros behind xs: target of inactive LH lanes and of tail-lane over-reads
@@ -41,6 +41,11 @@
 #define ENG_UPB 4            // up-hop row gathers in flight per lane and block
 
 // ---- constant-bank tables (kernel parameter) -----------------------------------------------------
+// Measured on B200 (tools/micro/const_ws.cu): warp-uniform constant loads run at full rate while the
+// table working set stays below ~5 KB per SM; above it every miss goes to the GPC-level constant cache,
+// which the 148 SMs saturate (first version of this kernel, 18 KB of u16 / u32 tables: 91 % of the GCC
+// request peak, 3.6-4.8 ms instead of 2.0 ms on the 4x4 sector).  Hence one byte per list entry, one
+// byte of counts per list, running list pointers, and nothing in here that a phase does not walk.
 struct EngConst {
   int m, hb, n_dn, nq, nseg, nlh;
   int xs_elems, zoff;                 // padded class-major row (doubles); zoff = first zero slot
@@ -52,22 +57,24 @@ struct EngConst {
   uint16_t aptr[ENG_MAX_WARPS + 1], bptr[ENG_MAX_WARPS + 1], sptr[ENG_MAX_WARPS + 1];
   uint32_t task_a[ENG_MAX_TASKS];     // k | blk << 4 | T << 6 | r0 << 8 | nr << 16     (jj0 = 64 * blk)
   uint32_t task_b[ENG_MAX_TASKS];     // k | T << 6 | jj0 << 8 | njj << 16
-  uint32_t task_s[ENG_MAX_TASKS];     // first natural segment | count << 16
-  uint32_t ll_desc[ENG_MAX_Q];        // per (k, r): start | (# '+') << 16 | (# '-') << 24
-  uint32_t hh_desc[ENG_MAX_SEG];      // per class-major segment: the same
-  uint16_t ll_ent[ENG_MAX_ENT];       // 8 * r'
-  uint16_t hh_ent[ENG_MAX_ENT];       // P8[k] * jj'   (relative to the class)
-  uint16_t lhq[ENG_MAX_LH][ENG_MAX_Q];  // per (bond, (k, r)): 8 * r' | dl bit << 10 | parity(dl part) << 11 | valid << 12
-  uint16_t dl_of_q[ENG_MAX_Q];        // bit pattern of dl
-  uint32_t seg_nat[ENG_MAX_SEG];      // natural order: slot (doubles) | offset in the row << 14 | k << 28
+  uint32_t task_s[ENG_MAX_TASKS];     // staging: k | T << 6 | jj0 << 8 | njj << 16
+  uint16_t ll_start[ENG_MAX_Q];       // per (k, r): first entry of its list ('+' entries, then '-' entries)
+  uint16_t hh_start[ENG_MAX_SEG];     // per class-major segment: the same
+  uint8_t ll_cnt[ENG_MAX_Q];          // (# '+') | (# '-') << 4
+  uint8_t hh_cnt[ENG_MAX_SEG];
+  uint8_t ll_ent[ENG_MAX_ENT];        // r'
+  uint8_t hh_ent[ENG_MAX_ENT];        // jj'
+  uint8_t lh_off[ENG_MAX_LH][ENG_MAX_Q];  // per (bond, (k, r)): r' (rank of dl ^ bit in the source class)
+  uint8_t lh_flg[ENG_MAX_Q];          // bit b = value of the dl bit of LH bond b; bit 4 + b = parity of its dl part
   uint16_t goff_cm[ENG_MAX_SEG];      // class-major segment -> offset in the row
 };
 
-// ---- per-lane tables (global memory, read once per task) ----------------------------------------
+// ---- per-lane tables (global memory, read once per task / per row) --------------------------------
 struct EngLane {
-  const uint16_t* dh_cm;     // [nseg]       dh bits of the class-major segment
-  const uint32_t* lh_lane;   // [nlh][nseg]  slot of the segment dh ^ bit (doubles; the zero region when its
-                             //              class is empty) | dh bit << 14 | parity(dh part) << 15
+  const uint16_t* dh_cm;     // [nseg]  dh bits of the class-major segment
+  const uint16_t* dl_of_q;   // [nq]    dl bits of the class-major column
+  const uint4* lh_lane;      // [nseg]  one word per LH bond: slot of the segment dh ^ bit (doubles; the zero
+                             //         region when its class is empty) | dh bit << 14 | parity(dh part) << 15
 };
 
 struct EngArgs {
@@ -107,80 +114,116 @@ inline double eng_flip(double v, uint32_t signmask) {
 template <typename T> inline T eng_ldg(const T* p) { return *p; }
 #endif
 
+// ---- hop-list walk with the entry count as a compile-time constant: straight-line code, one
+//      LDCU.U16 + T x (LDS.64 [Rlane + UR (+ 256 t)], DADD) per entry, no loop control ----
+template <int T, int N, bool NEG, bool HH>
+ENG_HD void eng_acc(const EngConst& C, int i, eng_addr scale, const eng_addr* base, double* acc) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    // LL: entry = r', byte offset 8 r'; HH: entry = jj', byte offset P8[k] * jj' (uniform multiply)
+    const eng_addr e = HH ? (eng_addr)C.hh_ent[i + j] * scale : (eng_addr)C.ll_ent[i + j] * 8u;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const double v = eng_ld(HH ? base[0] + e + 256u * t : base[t] + e);
+      if (NEG) acc[t] -= v; else acc[t] += v;
+    }
+  }
+}
+template <int T, bool NEG, bool HH>
+ENG_HD void eng_list(const EngConst& C, int i, int n, eng_addr scale, const eng_addr* base, double* acc) {
+  // (short lists dominate: '+' and '-' parts average 2.6 entries on the 4x4 lattice)
+  switch (n) {
+    case 0: break;
+    case 1: eng_acc<T, 1, NEG, HH>(C, i, scale, base, acc); break;
+    case 2: eng_acc<T, 2, NEG, HH>(C, i, scale, base, acc); break;
+    case 3: eng_acc<T, 3, NEG, HH>(C, i, scale, base, acc); break;
+    default:
+      eng_acc<T, 4, NEG, HH>(C, i, scale, base, acc);
+#pragma unroll 1
+      for (int j = 4; j < n; ++j) eng_acc<T, 1, NEG, HH>(C, i + j, scale, base, acc);
+  }
+}
+
+// LH hops of one column: bond b reads the per-lane source a1 (dl bit set: the lane's dh bit must be clear)
+// or a0 (dl bit clear); lanes whose dh bit does not fit read the zero region
+template <int T, int NLH>
+ENG_HD void eng_lh(const EngConst& C, int q, const eng_addr (*a0)[T], const eng_addr (*a1)[T],
+                   const uint32_t (*sg)[T], double* acc) {
+  // NLH is a compile-time bound (1, 2 or 4 >= the number of LH bonds; the tables of the missing bonds
+  // point at the zero region): a branch per bond would cut the column into basic blocks and ptxas
+  // then serialises LDS -> LOP3 -> DADD of every bond on one register pair (measured: short-scoreboard
+  // stalls 14.9 per issued instruction, 3.6 ms instead of 2.0 ms on the 4x4 sector)
+  const uint32_t flg = C.lh_flg[q];
+  double v[NLH][T];
+#pragma unroll
+  for (int b = 0; b < NLH; ++b) {
+    const eng_addr off = (eng_addr)C.lh_off[b][q] * 8u;
+    const bool set = ((flg >> b) & 1u) != 0u;
+#pragma unroll
+    for (int t = 0; t < T; ++t) v[b][t] = eng_ld((set ? a1[b][t] : a0[b][t]) + off);
+  }
+#pragma unroll
+  for (int b = 0; b < NLH; ++b) {
+    const uint32_t sl = ((flg >> (4 + b)) & 1u) << 31;
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] += eng_flip(v[b][t], sg[b][t] ^ sl);
+  }
+}
+
 // ---- phase A: one task = nr consecutive columns r of class k, T blocks of 32 segments (lanes along jj) ----
 // ys[(jj, r)] = (diag / hop) * x + sum_LL +- x[(jj, r')] + sum_LH +- x[(jj', r')]
-template <int T>
+// dg_a: per-row diagonal tables in shared memory, dgl[q] (doubles 0 .. ENG_MAX_Q) then dgh[segment]
+template <int T, int NLH>
 ENG_HD void eng_task_a(const EngConst& C, const EngLane& ln, uint32_t task, eng_addr xs_a, eng_addr ydelta,
-                       uint32_t ups, double eu_s, double u0_s, int lane) {
+                       eng_addr dg_a, int lane) {
   const int k = (int)(task & 15u), jj0 = (int)((task >> 4) & 3u) * 64;
   const int r0 = (int)((task >> 8) & 255u), nr = (int)((task >> 16) & 255u);
-  const int hk = C.H[k], nlh = C.nlh;
+  const int hk = C.H[k];
   const eng_addr pk8 = (eng_addr)C.P8[k], cb = xs_a + (eng_addr)C.xb8[k];
   const eng_addr zaddr = xs_a + (eng_addr)C.zoff * 8u;
   const int sgb = C.hoff[k], q0 = C.qoff[k];
   eng_addr xa[T];
   double dgh[T];
   bool live[T];
-  eng_addr a0[ENG_MAX_LH][T], a1[ENG_MAX_LH][T];
-  uint32_t sg[ENG_MAX_LH][T];
+  eng_addr a0[NLH][T], a1[NLH][T];
+  uint32_t sg[NLH][T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int jj = jj0 + lane + 32 * t;
     live[t] = jj < hk;
     const int jc = live[t] ? jj : hk - 1;   // lanes past the class recompute its last segment, never store
     xa[t] = cb + (eng_addr)jc * pk8;
-    const uint32_t dhb = (uint32_t)eng_ldg(ln.dh_cm + sgb + jc) << C.m;
-    dgh[t] = eu_s + u0_s * (double)eng_popc(ups & dhb);
+    dgh[t] = eng_ld(dg_a + (eng_addr)(ENG_MAX_Q + sgb + jc) * 8u);
+    const uint4 w4 = eng_ldg(ln.lh_lane + sgb + jc);
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int b = 0; b < ENG_MAX_LH; ++b) {
-      a0[b][t] = zaddr; a1[b][t] = zaddr; sg[b][t] = 0u;
-      if (b < nlh) {
-        const uint32_t w = eng_ldg(ln.lh_lane + (size_t)b * C.nseg + sgb + jc);
-        const eng_addr src = xs_a + (eng_addr)(w & 0x3fffu) * 8u;
-        if (w & 0x4000u) a0[b][t] = src; else a1[b][t] = src;   // dl bit clear needs the dh bit set, and v.v.
-        sg[b][t] = (w >> 15) << 31;
-      }
+    for (int b = 0; b < NLH; ++b) {
+      const eng_addr src = xs_a + (eng_addr)(w[b] & 0x3fffu) * 8u;
+      const bool bit = (w[b] & 0x4000u) != 0u;
+      a0[b][t] = bit ? src : zaddr;    // dl bit clear needs the dh bit set ...
+      a1[b][t] = bit ? zaddr : src;    // ... and vice versa
+      sg[b][t] = (w[b] >> 15) << 31;
+#ifdef __CUDA_ARCH__
+      // keep both candidates in registers (otherwise ptxas re-derives them from w in every column)
+      asm volatile("" : "+r"(a0[b][t]), "+r"(a1[b][t]), "+r"(sg[b][t]));
+#endif
     }
   }
 #pragma unroll 1
   for (int r = r0; r < r0 + nr; ++r) {
     const int q = q0 + r;
-    const uint32_t d = C.ll_desc[q];
-    int i = (int)(d & 0xffffu);
-    const int ie = i + (int)((d >> 16) & 0xffu), je = ie + (int)(d >> 24);
+    // (list pointer and counts re-read per column: a pointer carried from column to column ends up in
+    //  a vector register and drags the whole list walk off the uniform datapath)
+    const int i = (int)C.ll_start[q];
+    const uint32_t d = C.ll_cnt[q];
+    const int np = (int)(d & 15u), nn = (int)(d >> 4);
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-#pragma unroll 4
-    for (; i < ie; ++i) {
-      const eng_addr e = (eng_addr)C.ll_ent[i];
-#pragma unroll
-      for (int t = 0; t < T; ++t) acc[t] += eng_ld(xa[t] + e);
-    }
-#pragma unroll 4
-    for (; i < je; ++i) {
-      const eng_addr e = (eng_addr)C.ll_ent[i];
-#pragma unroll
-      for (int t = 0; t < T; ++t) acc[t] -= eng_ld(xa[t] + e);
-    }
-#pragma unroll
-    for (int b = 0; b < ENG_MAX_LH; ++b) {
-      if (b < nlh) {
-        const uint32_t w = C.lhq[b][q];
-        if (w & 0x1000u) {
-          const eng_addr off = (eng_addr)(w & 0x3ffu);
-          const uint32_t sl = (w & 0x800u) << 20;
-          if (w & 0x400u) {
-#pragma unroll
-            for (int t = 0; t < T; ++t) acc[t] += eng_flip(eng_ld(a1[b][t] + off), sg[b][t] ^ sl);
-          } else {
-#pragma unroll
-            for (int t = 0; t < T; ++t) acc[t] += eng_flip(eng_ld(a0[b][t] + off), sg[b][t] ^ sl);
-          }
-        }
-      }
-    }
-    const double dgl = u0_s * (double)eng_popc(ups & (uint32_t)C.dl_of_q[q]);
+    eng_list<T, false, false>(C, i, np, 8u, xa, acc);
+    eng_list<T, true, false>(C, i + np, nn, 8u, xa, acc);
+    eng_lh<T, NLH>(C, q, a0, a1, sg, acc);
+    const double dgl = eng_ld(dg_a + (eng_addr)q * 8u);
     const eng_addr r8 = (eng_addr)r * 8u;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -191,13 +234,23 @@ ENG_HD void eng_task_a(const EngConst& C, const EngLane& ln, uint32_t task, eng_
   }
 }
 
+template <int NLH>
 ENG_HD void eng_run_a(const EngConst& C, const EngLane& ln, int warp, eng_addr xs_a, eng_addr ydelta,
-                      uint32_t ups, double eu_s, double u0_s, int lane) {
+                      eng_addr dg_a, int lane) {
   for (int it = C.aptr[warp]; it < C.aptr[warp + 1]; ++it) {
     const uint32_t task = C.task_a[it];
-    if (((task >> 6) & 3u) == 1u) eng_task_a<1>(C, ln, task, xs_a, ydelta, ups, eu_s, u0_s, lane);
-    else eng_task_a<2>(C, ln, task, xs_a, ydelta, ups, eu_s, u0_s, lane);
+    if (((task >> 6) & 3u) == 1u) eng_task_a<1, NLH>(C, ln, task, xs_a, ydelta, dg_a, lane);
+    else eng_task_a<2, NLH>(C, ln, task, xs_a, ydelta, dg_a, lane);
   }
+}
+// smallest compiled LH bound >= nlh
+static inline int eng_nlh_bound(int nlh) { return nlh <= 1 ? 1 : nlh <= 2 ? 2 : 4; }
+
+// the per-row diagonal tables: dgl[q] = (u / hop) popc(ups & dl), dgh[s] = eu / hop + (u / hop) popc(ups & dh)
+ENG_HD void eng_fill_diag(const EngConst& C, const EngLane& ln, double* dg, int i, uint32_t ups, double eu_s,
+                          double u0_s) {
+  if (i < C.nq) dg[i] = u0_s * (double)eng_popc(ups & (uint32_t)eng_ldg(ln.dl_of_q + i));
+  if (i < C.nseg) dg[ENG_MAX_Q + i] = eu_s + u0_s * (double)eng_popc(ups & ((uint32_t)eng_ldg(ln.dh_cm + i) << C.m));
 }
 
 // row-uniform data of phase B's epilogue
@@ -221,43 +274,35 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
   const int k = (int)(task & 15u), jj0 = (int)((task >> 8) & 255u), njj = (int)((task >> 16) & 255u);
   const int sk = C.S[k], sgb = C.hoff[k];
   const eng_addr pk8 = (eng_addr)C.P8[k];
-  const eng_addr xl = xs_a + (eng_addr)C.xb8[k] + (eng_addr)lane * 8u;
+  const eng_addr xl[1] = {xs_a + (eng_addr)C.xb8[k] + (eng_addr)lane * 8u};
+  const double* xrl = E.xr + lane;
+  double* yrl = E.yr + lane;
   bool live[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) live[t] = lane + 32 * t < sk;
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + njj; ++jj) {
     const int sgi = sgb + jj;
-    const uint32_t d = C.hh_desc[sgi];
+    const int i = (int)C.hh_start[sgi];
+    const uint32_t d = C.hh_cnt[sgi];
     const int goff = (int)C.goff_cm[sgi];
     double up[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) up[t] = 0.0;
     double g0[ENG_UPB][T];
-    if (WITH_UP) {   // first batch of up-hop gathers: issued here, consumed behind the hop loops
+    if (WITH_UP) {   // first batch of up-hop gathers: issued here, consumed behind the hop lists
 #pragma unroll
       for (int q = 0; q < ENG_UPB; ++q)
 #pragma unroll
         for (int t = 0; t < T; ++t)
-          g0[q][t] = (q < E.cu && live[t]) ? eng_ldg(E.xr + E.up_off[q] + goff + lane + 32 * t) : 0.0;
+          g0[q][t] = (q < E.cu && live[t]) ? eng_ldg(xrl + E.up_off[q] + goff + 32 * t) : 0.0;
     }
-    int i = (int)(d & 0xffffu);
-    const int ie = i + (int)((d >> 16) & 0xffu), je = ie + (int)(d >> 24);
+    const int np = (int)(d & 15u), nn = (int)(d >> 4);
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-#pragma unroll 4
-    for (; i < ie; ++i) {
-      const eng_addr e = (eng_addr)C.hh_ent[i];
-#pragma unroll
-      for (int t = 0; t < T; ++t) acc[t] += eng_ld(xl + e + 256u * t);
-    }
-#pragma unroll 4
-    for (; i < je; ++i) {
-      const eng_addr e = (eng_addr)C.hh_ent[i];
-#pragma unroll
-      for (int t = 0; t < T; ++t) acc[t] -= eng_ld(xl + e + 256u * t);
-    }
+    eng_list<T, false, true>(C, i, np, pk8, xl, acc);
+    eng_list<T, true, true>(C, i + np, nn, pk8, xl, acc);
     if (WITH_UP) {
 #pragma unroll
       for (int q = 0; q < ENG_UPB; ++q)
@@ -273,7 +318,7 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
         for (int q = 0; q < ENG_UPB; ++q)
 #pragma unroll
           for (int t = 0; t < T; ++t)
-            g[q][t] = (qb + q < E.cu && live[t]) ? eng_ldg(E.xr + E.up_off[qb + q] + goff + lane + 32 * t) : 0.0;
+            g[q][t] = (qb + q < E.cu && live[t]) ? eng_ldg(xrl + E.up_off[qb + q] + goff + 32 * t) : 0.0;
 #pragma unroll
         for (int q = 0; q < ENG_UPB; ++q)
           if (qb + q < E.cu) {
@@ -283,12 +328,12 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
           }
       }
     }
-    const eng_addr own = xl + (eng_addr)jj * pk8;
+    const eng_addr own = xl[0] + (eng_addr)jj * pk8;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const double a = E.hop0 * (eng_ld(own + ydelta + 256u * t) + acc[t]) + up[t];
       if (live[t]) {
-        double* yp = E.yr + goff + lane + 32 * t;
+        double* yp = yrl + goff + 32 * t;
         if (LZ) {
           double w = E.s1 * a;
           if (E.has_prev) w -= E.s2 * *yp;
@@ -320,18 +365,30 @@ __device__ __forceinline__ void eng_cp_async8(uint32_t dst, const double* src) {
 }
 
 // smem: [xs: xs_elems + ENG_ZREG doubles][ys: xs_elems + ENG_ZREG doubles]
-template <bool LZ, bool WITH_UP, int NT>
-__global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ EngConst C, const EngArgs A) {
+// TAB_SMEM: the tables are copied to shared memory once per CTA and walked with (broadcast) LDS instead
+// of constant loads -- the constant caches of an SM hold ~5 KB and the 4x4 lattice needs more (see EngConst)
+template <bool LZ, bool WITH_UP, int NT, int NLH, bool TAB_SMEM = true>
+__global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ EngConst Cc, const EngArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TAB_BYTES = TAB_SMEM ? (int)((sizeof(EngConst) + 15) & ~(size_t)15) : 0;
+  if (TAB_SMEM) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&Cc);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(EngConst) / 4); i += NT) dst[i] = src[i];
+    __syncthreads();
+  }
+  const EngConst& C = TAB_SMEM ? *reinterpret_cast<const EngConst*>(smem_raw) : Cc;
   __shared__ double red[32];
-  __shared__ i64 s_up_off[ELL_MAX_BONDS];
-  __shared__ double s_up_coef[ELL_MAX_BONDS];
+  __shared__ double s_dg[ENG_MAX_Q + ENG_MAX_SEG];
+  __shared__ i64 s_up_off[WITH_UP ? ELL_MAX_BONDS : 1];
+  __shared__ double s_up_coef[WITH_UP ? ELL_MAX_BONDS : 1];
   const HubParams& p = A.hp;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for ptxas: tables walk the uniform datapath
-  double* xs = reinterpret_cast<double*>(smem_raw);
+  double* xs = reinterpret_cast<double*>(smem_raw + TAB_BYTES);
   const int xs_total = C.xs_elems + ENG_ZREG;
   const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(xs);
+  const uint32_t dg_a = (uint32_t)__cvta_generic_to_shared(s_dg);
   const uint32_t ydelta = (uint32_t)xs_total * 8u;
   for (int i = tid; i < 2 * xs_total; i += NT) xs[i] = 0.0;   // slack slots and the zero region stay 0
   int j; double s1, s2; bool has_prev;
@@ -343,24 +400,27 @@ __global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ 
   EngEpi E;
   E.hop0 = p.hop0; E.accumulate = p.accumulate; E.s1 = s1; E.s2 = s2; E.has_prev = has_prev;
   E.up_off = s_up_off; E.up_coef = s_up_coef; E.cu = 0;
+  const uint32_t dst_l = xs_a + (uint32_t)lane * 8u;
   __syncthreads();
   for (i64 row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     const i64 u = p.row0 + row;
     const double* __restrict__ xr = p.x + row * nd;
     E.xr = xr; E.yr = p.y + row * nd;
+    const double* src_l = xr + lane;
     // ---- stage the row: natural order -> class-major padded layout, one segment per warp pass ----
     for (int it = C.sptr[warp]; it < C.sptr[warp + 1]; ++it) {
       const uint32_t ts = C.task_s[it];
-      const int sA = (int)(ts & 0xffffu), sB = sA + (int)(ts >> 16);
+      const int k = (int)(ts & 15u), jA = (int)((ts >> 8) & 255u), jB = jA + (int)((ts >> 16) & 255u);
+      const int sk = C.S[k], sgb = C.hoff[k];
+      const uint32_t pk8 = (uint32_t)C.P8[k], dst_k = dst_l + (uint32_t)C.xb8[k];
+      const bool l0 = lane < sk, l1 = lane + 32 < sk, l2 = lane + 64 < sk;
 #pragma unroll 1
-      for (int s = sA; s < sB; ++s) {
-        const uint32_t w = C.seg_nat[s];
-        const uint32_t dst = xs_a + (w & 0x3fffu) * 8u + (uint32_t)lane * 8u;
-        const double* src = xr + ((w >> 14) & 0x3fffu) + lane;
-        const int sk = C.S[w >> 28];
-        if (lane < sk) eng_cp_async8(dst, src);
-        if (lane + 32 < sk) eng_cp_async8(dst + 256u, src + 32);
-        if (lane + 64 < sk) eng_cp_async8(dst + 512u, src + 64);
+      for (int jj = jA; jj < jB; ++jj) {
+        const uint32_t dst = dst_k + (uint32_t)jj * pk8;
+        const double* src = src_l + (int)C.goff_cm[sgb + jj];
+        if (l0) eng_cp_async8(dst, src);
+        if (l1) eng_cp_async8(dst + 256u, src + 32);
+        if (l2) eng_cp_async8(dst + 512u, src + 64);
       }
     }
     if (WITH_UP) {
@@ -372,14 +432,13 @@ __global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ 
         s_up_coef[q] = (e >> 31) ? -p.hop0 : p.hop0;
       }
     }
-    const uint32_t ups = p.up_states[u];
-    const double eu_s = (p.e_up[u] + A.e_dn_const) * inv_hop;
+    eng_fill_diag(C, A.ln, s_dg, tid, p.up_states[u], (p.e_up[u] + A.e_dn_const) * inv_hop, u0_s);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    eng_run_a(C, A.ln, warp, xs_a, ydelta, ups, eu_s, u0_s, lane);
+    eng_run_a<NLH>(C, A.ln, warp, xs_a, ydelta, dg_a, lane);
     __syncthreads();
     eng_run_b<LZ, WITH_UP>(C, warp, xs_a, ydelta, E, dot, lane);
-    __syncthreads();   // xs / ys of this row fully consumed
+    __syncthreads();   // xs / ys / s_dg of this row fully consumed
   }
   lz_finish<LZ>(p.lz, j, dot, red);
 }
@@ -390,7 +449,7 @@ __global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 struct EngHost {
   EngConst C;
-  std::vector<uint16_t> dh_cm;
+  std::vector<uint16_t> dh_cm, dl_q;
   std::vector<uint32_t> lh_lane;
   bool ok = false;
   double e_dn_const = 0.0;
@@ -399,32 +458,35 @@ struct EngHost {
 };
 
 // Longest-processing-time-first assignment of cost-weighted pieces to warps; fills ptr / tasks.
-static bool eng_assign(const std::vector<std::pair<double, uint32_t>>& pieces, int nwarps, uint16_t* ptr,
-                       uint32_t* tasks, int& ntasks_total, int cap) {
+struct EngPiece { double cost; uint32_t task; uint16_t start; };
+static bool eng_assign(const std::vector<EngPiece>& pieces, int nwarps, uint16_t* ptr, uint32_t* tasks,
+                       uint16_t* starts, int cap) {
   std::vector<size_t> order(pieces.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(),
-                   [&](size_t a, size_t b) { return pieces[a].first > pieces[b].first; });
+                   [&](size_t a, size_t b) { return pieces[a].cost > pieces[b].cost; });
   std::vector<double> load(nwarps, 0.0);
-  std::vector<std::vector<uint32_t>> mine(nwarps);
+  std::vector<std::vector<size_t>> mine(nwarps);
   for (size_t oi : order) {
     int best = 0;
     for (int w = 1; w < nwarps; ++w)
       if (load[w] < load[best]) best = w;
-    load[best] += pieces[oi].first;
-    mine[best].push_back(pieces[oi].second);
+    load[best] += pieces[oi].cost;
+    mine[best].push_back(oi);
   }
   int n = 0;
   for (int w = 0; w < ENG_MAX_WARPS + 1; ++w) ptr[w] = 0;
   for (int w = 0; w < nwarps; ++w) {
     ptr[w] = (uint16_t)n;
-    for (uint32_t t : mine[w]) {
+    std::sort(mine[w].begin(), mine[w].end());   // class-major order inside a warp
+    for (size_t oi : mine[w]) {
       if (n >= cap) return false;
-      tasks[n++] = t;
+      tasks[n] = pieces[oi].task;
+      if (starts) starts[n] = pieces[oi].start;
+      ++n;
     }
   }
   for (int w = nwarps; w <= ENG_MAX_WARPS; ++w) ptr[w] = (uint16_t)n;
-  ntasks_total = n;
   return true;
 }
 
@@ -462,8 +524,8 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
   const int nseg = ho;
   C.nseg = nseg;
   if (xoff + ENG_ZREG >= 16384 || nseg > ENG_MAX_SEG || nseg < 1) return CMPY_OK;
-  T.smem = sizeof(double) * 2 * ((size_t)xoff + ENG_ZREG);
-  if ((i64)T.smem + 2048 > smem_optin) return CMPY_OK;
+  T.smem = sizeof(double) * 2 * ((size_t)xoff + ENG_ZREG) + ((sizeof(EngConst) + 15) & ~(size_t)15);
+  if ((i64)T.smem + 6144 > smem_optin) return CMPY_OK;   // + static shared memory of the kernel
   // ranks of dl / dh inside their classes
   std::vector<int> lo_rank(nlo), dl_of_q(nlo), k_of_q(nlo);
   {
@@ -488,8 +550,6 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
       hi_jj[dh] = fill[k];
       hi_cm[dh] = C.hoff[k] + fill[k];
       dh_cm[hi_cm[dh]] = dh;
-      const int slot = C.xb8[k] / 8 + fill[k] * (C.P8[k] / 8);
-      C.seg_nat[ordinal] = (uint32_t)slot | ((uint32_t)off << 14) | ((uint32_t)k << 28);
       C.goff_cm[hi_cm[dh]] = (uint16_t)off;
       ++fill[k];
       off += C.S[k];
@@ -510,45 +570,50 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
   auto parity = [&](u64 state, int a, int b2) {
     return __builtin_popcountll(state & between_mask(a, b2, sign_width)) & 1;
   };
-  // hop lists: '+' entries, then '-' entries
+  // hop lists: '+' entries, then '-' entries; the lists of consecutive columns / segments follow each other
   int nle = 0, nhe = 0;
-  std::vector<int> n_ll(nlo, 0), n_hh(nseg, 0);
+  std::vector<int> n_ll(nlo, 0), n_hh(nseg, 0), ll_start(nlo + 1, 0), hh_start(nseg + 1, 0);
   for (int q = 0; q < nlo; ++q) {
     const int dl = dl_of_q[q];
-    std::vector<uint16_t> pos, neg;
+    std::vector<uint8_t> pos, neg;
     for (int b : ll) {
       const int b1 = (dl >> s1[b]) & 1, b2 = (dl >> s2[b]) & 1;
       if (b1 == b2) continue;
       const int nl = dl ^ (1 << s1[b]) ^ (1 << s2[b]);
-      (parity((u64)dl, s1[b], s2[b]) ? neg : pos).push_back((uint16_t)(8 * lo_rank[nl]));
+      (parity((u64)dl, s1[b], s2[b]) ? neg : pos).push_back((uint8_t)lo_rank[nl]);
     }
-    if (nle + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 255 || neg.size() > 255) return CMPY_OK;
-    C.ll_desc[q] = (uint32_t)nle | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 24);
-    for (uint16_t v : pos) C.ll_ent[nle++] = v;
-    for (uint16_t v : neg) C.ll_ent[nle++] = v;
+    if (nle + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 15 || neg.size() > 15) return CMPY_OK;
+    ll_start[q] = nle; C.ll_start[q] = (uint16_t)nle;
+    C.ll_cnt[q] = (uint8_t)(pos.size() | (neg.size() << 4));
+    for (uint8_t v : pos) C.ll_ent[nle++] = v;
+    for (uint8_t v : neg) C.ll_ent[nle++] = v;
     n_ll[q] = (int)(pos.size() + neg.size());
   }
+  ll_start[nlo] = nle;
   for (int sgi = 0; sgi < nseg; ++sgi) {
-    const int dh = dh_cm[sgi], k = hi_k[dh];
-    std::vector<uint16_t> pos, neg;
+    const int dh = dh_cm[sgi];
+    std::vector<uint8_t> pos, neg;
     for (int b : hh) {
       const int a = s1[b] - m, c = s2[b] - m;
       const int b1 = (dh >> a) & 1, b2 = (dh >> c) & 1;
       if (b1 == b2) continue;
       const int nh = dh ^ (1 << a) ^ (1 << c);
-      (parity((u64)dh << m, s1[b], s2[b]) ? neg : pos).push_back((uint16_t)(hi_jj[nh] * C.P8[k]));
+      (parity((u64)dh << m, s1[b], s2[b]) ? neg : pos).push_back((uint8_t)hi_jj[nh]);
     }
-    if (nhe + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 255 || neg.size() > 255) return CMPY_OK;
-    C.hh_desc[sgi] = (uint32_t)nhe | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 24);
-    for (uint16_t v : pos) C.hh_ent[nhe++] = v;
-    for (uint16_t v : neg) C.hh_ent[nhe++] = v;
+    if (nhe + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 15 || neg.size() > 15) return CMPY_OK;
+    hh_start[sgi] = nhe; C.hh_start[sgi] = (uint16_t)nhe;
+    C.hh_cnt[sgi] = (uint8_t)(pos.size() | (neg.size() << 4));
+    for (uint8_t v : pos) C.hh_ent[nhe++] = v;
+    for (uint8_t v : neg) C.hh_ent[nhe++] = v;
     n_hh[sgi] = (int)(pos.size() + neg.size());
   }
-  for (int q = 0; q < nlo; ++q) C.dl_of_q[q] = (uint16_t)dl_of_q[q];
-  // LH tables: warp-uniform part per (bond, (k, r)), per-lane part per (bond, class-major segment)
+  hh_start[nseg] = nhe;
+  T.dl_q.assign(nlo, 0);
+  for (int q = 0; q < nlo; ++q) T.dl_q[q] = (uint16_t)dl_of_q[q];
+  // LH tables: warp-uniform part per (bond, (k, r)), per-lane part per class-major segment (4 bonds packed)
   T.dh_cm.assign(nseg, 0);
   for (int sgi = 0; sgi < nseg; ++sgi) T.dh_cm[sgi] = (uint16_t)dh_cm[sgi];
-  T.lh_lane.assign((size_t)std::max(1, C.nlh) * nseg, (uint32_t)C.zoff);
+  T.lh_lane.assign((size_t)4 * nseg, (uint32_t)C.zoff);
   std::vector<int> n_lh(nlo, 0);
   for (int qb = 0; qb < C.nlh; ++qb) {
     const int b = lh[qb];
@@ -559,90 +624,82 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
       const uint32_t bit = (uint32_t)((dh >> c) & 1);
       const uint32_t par = (uint32_t)parity((u64)dh << m, m - 1, s2[b]);   // bits of dh strictly below c
       const uint32_t src = (hi_k[nh] >= 0) ? (uint32_t)slot_of(nh) : (uint32_t)C.zoff;
-      T.lh_lane[(size_t)qb * nseg + sgi] = src | (bit << 14) | (par << 15);
+      T.lh_lane[(size_t)4 * sgi + qb] = src | (bit << 14) | (par << 15);
     }
     for (int q = 0; q < nlo; ++q) {
       const int dl = dl_of_q[q], k = k_of_q[q];
       const int bit_lo = (dl >> a) & 1;
       const int kp = k + (bit_lo ? -1 : 1);   // class of the source segment
-      uint16_t e = 0;
+      C.lh_flg[q] = (uint8_t)(C.lh_flg[q] | (bit_lo << qb));
+      C.lh_off[qb][q] = 0;   // source class empty: the lanes point at the zero region
       if (kp >= 0 && kp <= m && C.H[kp] > 0 && C.H[k] > 0) {
         const int nl = dl ^ (1 << a);
-        const int par = parity((u64)dl, a, m);   // bits of dl strictly above a
-        e = (uint16_t)((8 * lo_rank[nl]) | (bit_lo << 10) | (par << 11) | (1 << 12));
+        C.lh_off[qb][q] = (uint8_t)lo_rank[nl];
+        if (parity((u64)dl, a, m)) C.lh_flg[q] = (uint8_t)(C.lh_flg[q] | (16 << qb));   // bits of dl strictly above a
         n_lh[q] += 1;
       }
-      C.lhq[qb][q] = e;
     }
   }
   // ---- tasks: cost-balanced pieces, longest first.  Costs = issued instructions of the compiled loops ----
   {
-    std::vector<std::pair<double, uint32_t>> pa, pb, ps;
-    double tot_a = 0.0, tot_b = 0.0;
-    auto cost_a = [&](int k, int r, int Tt) {
+    std::vector<EngPiece> pa, pb, ps;
+    double tot_a = 0.0, tot_b = 0.0, tot_s = 0.0;
+    const int nlhb = eng_nlh_bound(C.nlh);
+    auto cost_a = [&](int k, int r, int Tt) {   // per column: header + lists + LH + diagonal / store
       const int q = C.qoff[k] + r;
-      return 6.0 + Tt * (6.0 + 2.0 * n_ll[q] + 3.0 * n_lh[q]) + n_ll[q] + 2.0 * C.nlh;
+      return 14.0 + n_ll[q] * (2.0 + 2.0 * Tt) + 6.0 + nlhb * (3.0 + 4.0 * Tt) + 1.0 + 4.0 * Tt;
     };
     auto cost_b = [&](int k, int jj) {
       const int Tt = (C.S[k] + 31) / 32;
       const int sgi = C.hoff[k] + jj;
-      return 8.0 + Tt * (7.0 + 2.0 * n_hh[sgi] + (with_up_cost ? 40.0 : 0.0)) + n_hh[sgi];
+      return 16.0 + n_hh[sgi] * (2.0 + 2.0 * Tt) + 6.0 * Tt + (with_up_cost ? 40.0 * Tt : 0.0);
     };
+    auto cost_s = [&](int k) { return 4.0 + 2.0 * ((C.S[k] + 31) / 32); };
     for (int k = 0; k <= m; ++k) {
       if (C.H[k] <= 0) continue;
       for (int blk = 0; blk * 64 < C.H[k]; ++blk) {
         const int Tt = (std::min(C.H[k] - blk * 64, 64) + 31) / 32;
         for (int r = 0; r < C.S[k]; ++r) tot_a += cost_a(k, r, Tt);
       }
-      for (int jj = 0; jj < C.H[k]; ++jj) tot_b += cost_b(k, jj);
+      for (int jj = 0; jj < C.H[k]; ++jj) { tot_b += cost_b(k, jj); tot_s += cost_s(k); }
     }
-    const double tgt_a = tot_a / (3.0 * nwarps) + 40.0, tgt_b = tot_b / (3.0 * nwarps) + 20.0;
+    const double tgt_a = tot_a / (2.0 * nwarps) + 30.0, tgt_b = tot_b / (2.0 * nwarps) + 10.0;
+    const double tgt_s = tot_s / (1.5 * nwarps) + 4.0;
     for (int k = 0; k <= m; ++k) {
       if (C.H[k] <= 0) continue;
       for (int blk = 0; blk * 64 < C.H[k]; ++blk) {
         const int Tt = (std::min(C.H[k] - blk * 64, 64) + 31) / 32;
         int r0 = 0;
-        double acc = 40.0 * Tt;   // per-task set-up (hoisted per-lane state)
+        double acc = 30.0 + 25.0 * Tt;   // per-task set-up (hoisted per-lane state)
         for (int r = 0; r < C.S[k]; ++r) {
           acc += cost_a(k, r, Tt);
           if (acc >= tgt_a || r + 1 == C.S[k]) {
             pa.push_back({acc, (uint32_t)k | ((uint32_t)blk << 4) | ((uint32_t)Tt << 6) | ((uint32_t)r0 << 8) |
-                                   ((uint32_t)(r + 1 - r0) << 16)});
-            r0 = r + 1; acc = 40.0 * Tt;
+                                   ((uint32_t)(r + 1 - r0) << 16), (uint16_t)ll_start[C.qoff[k] + r0]});
+            r0 = r + 1; acc = 30.0 + 25.0 * Tt;
           }
         }
       }
-      {
-        const int Tt = (C.S[k] + 31) / 32;
-        int j0 = 0;
-        double acc = 12.0;
-        for (int jj = 0; jj < C.H[k]; ++jj) {
-          acc += cost_b(k, jj);
-          if (acc >= tgt_b || jj + 1 == C.H[k]) {
-            pb.push_back({acc, (uint32_t)k | ((uint32_t)Tt << 6) | ((uint32_t)j0 << 8) | ((uint32_t)(jj + 1 - j0) << 16)});
-            j0 = jj + 1; acc = 12.0;
-          }
+      const int Tt = (C.S[k] + 31) / 32;
+      int j0 = 0, j0s = 0;
+      double acc = 12.0, accs = 8.0;
+      for (int jj = 0; jj < C.H[k]; ++jj) {
+        acc += cost_b(k, jj);
+        if (acc >= tgt_b || jj + 1 == C.H[k]) {
+          pb.push_back({acc, (uint32_t)k | ((uint32_t)Tt << 6) | ((uint32_t)j0 << 8) | ((uint32_t)(jj + 1 - j0) << 16),
+                        (uint16_t)hh_start[C.hoff[k] + j0]});
+          j0 = jj + 1; acc = 12.0;
+        }
+        accs += cost_s(k);
+        if (accs >= tgt_s || jj + 1 == C.H[k]) {
+          ps.push_back({accs, (uint32_t)k | ((uint32_t)Tt << 6) | ((uint32_t)j0s << 8) | ((uint32_t)(jj + 1 - j0s) << 16), 0});
+          j0s = jj + 1; accs = 8.0;
         }
       }
     }
-    {  // staging: runs of natural segments, cost = 32-lane passes
-      double tot = 0.0;
-      for (int s = 0; s < nseg; ++s) tot += 3.0 + (C.S[C.seg_nat[s] >> 28] + 31) / 32;
-      const double tgt = tot / (2.0 * nwarps) + 4.0;
-      int s0 = 0;
-      double acc = 0.0;
-      for (int s = 0; s < nseg; ++s) {
-        acc += 3.0 + (C.S[C.seg_nat[s] >> 28] + 31) / 32;
-        if (acc >= tgt || s + 1 == nseg) {
-          ps.push_back({acc, (uint32_t)s0 | ((uint32_t)(s + 1 - s0) << 16)});
-          s0 = s + 1; acc = 0.0;
-        }
-      }
-    }
-    int na = 0, nb = 0, ns = 0;
-    if (!eng_assign(pa, nwarps, C.aptr, C.task_a, na, ENG_MAX_TASKS)) return CMPY_OK;
-    if (!eng_assign(pb, nwarps, C.bptr, C.task_b, nb, ENG_MAX_TASKS)) return CMPY_OK;
-    if (!eng_assign(ps, nwarps, C.sptr, C.task_s, ns, ENG_MAX_TASKS)) return CMPY_OK;
+    if (!eng_assign(pa, nwarps, C.aptr, C.task_a, nullptr, ENG_MAX_TASKS)) return CMPY_OK;
+    if (!eng_assign(pb, nwarps, C.bptr, C.task_b, nullptr, ENG_MAX_TASKS)) return CMPY_OK;
+    if (!eng_assign(ps, nwarps, C.sptr, C.task_s, nullptr, ENG_MAX_TASKS)) return CMPY_OK;
   }
   // energies: eps uniform -> eps * n_dn summed like weighted_element (ascending adds)
   { double v = 0; for (int i = 0; i < n_dn; ++i) v += eps[0]; T.e_dn_const = v; }

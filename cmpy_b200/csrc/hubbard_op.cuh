@@ -32,11 +32,12 @@ __global__ void narrow_states_kernel(const i64* __restrict__ in, i64 n, uint32_t
 struct EngTables {
   EngHost H;
   uint16_t* d_dh_cm = nullptr;
+  uint16_t* d_dl_q = nullptr;
   uint32_t* d_lh_lane = nullptr;
   bool ok = false;
   void release() {
-    cudaFree(d_dh_cm); cudaFree(d_lh_lane);
-    d_dh_cm = nullptr; d_lh_lane = nullptr; ok = false;
+    cudaFree(d_dh_cm); cudaFree(d_dl_q); cudaFree(d_lh_lane);
+    d_dh_cm = nullptr; d_dl_q = nullptr; d_lh_lane = nullptr; ok = false;
   }
 };
 
@@ -66,6 +67,8 @@ struct HubbardOp : cmpy_op_s {
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
   EngTables eng;             // generation-3 row engine (constant-bank hop lists)
   bool eng_full = false;     // variant 0 uses the engine for the full H.v too (up hops as row gathers)
+  int eng_threads = 1024;    // CTA size of the engine: 1024 threads x 64 registers (measured: 1.84 ms vs 2.02 ms
+                             // with 512 x 128 on the 4x4 sector, dn-only pass)
 
   ~HubbardOp() override {
     up.release(); dn.release(); seg.release(); cls.release(); lng.release(); cls2.release(); lng2.release();
@@ -228,15 +231,42 @@ struct HubbardOp : cmpy_op_s {
     return CMPY_OK;
   }
 
+  template <bool LZ, int NLH>
+  void launch_eng_n(const EngArgs& A, bool with_up, int g, cudaStream_t st) {
+    if (eng_threads == 512) {
+      if (with_up) hub_eng_kernel<LZ, true, 512, NLH><<<g, 512, eng.H.smem, st>>>(eng.H.C, A);
+      else hub_eng_kernel<LZ, false, 512, NLH><<<g, 512, eng.H.smem, st>>>(eng.H.C, A);
+    } else {
+      if (with_up) hub_eng_kernel<LZ, true, 1024, NLH><<<g, 1024, eng.H.smem, st>>>(eng.H.C, A);
+      else hub_eng_kernel<LZ, false, 1024, NLH><<<g, 1024, eng.H.smem, st>>>(eng.H.C, A);
+    }
+  }
+
+  template <int NLH>
+  int raise_eng_limits() {
+    int rc = raise_smem_limit(hub_eng_kernel<false, false, 512, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, false, 512, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<false, true, 512, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, true, 512, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<false, false, 1024, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, false, 1024, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<false, true, 1024, NLH>, smem_optin);
+    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, true, 1024, NLH>, smem_optin);
+    return rc;
+  }
+
   template <bool LZ>
   int launch_eng(HubParams& p, cudaStream_t st) {
     EngArgs A;
-    A.hp = p; A.ln.dh_cm = eng.d_dh_cm; A.ln.lh_lane = eng.d_lh_lane; A.e_dn_const = eng.H.e_dn_const;
+    A.hp = p; A.ln.dh_cm = eng.d_dh_cm; A.ln.dl_of_q = eng.d_dl_q; A.ln.lh_lane = reinterpret_cast<const uint4*>(eng.d_lh_lane); A.e_dn_const = eng.H.e_dn_const;
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
-    if (p.with_up) hub_eng_kernel<LZ, true, 1024><<<(int)g, 1024, eng.H.smem, st>>>(eng.H.C, A);
-    else hub_eng_kernel<LZ, false, 1024><<<(int)g, 1024, eng.H.smem, st>>>(eng.H.C, A);
+    switch (eng_nlh_bound(eng.H.C.nlh)) {
+      case 1: launch_eng_n<LZ, 1>(A, p.with_up != 0, (int)g, st); break;
+      case 2: launch_eng_n<LZ, 2>(A, p.with_up != 0, (int)g, st); break;
+      default: launch_eng_n<LZ, 4>(A, p.with_up != 0, (int)g, st); break;
+    }
     KERNEL_CHECK();
     return CMPY_OK;
   }
@@ -244,17 +274,19 @@ struct HubbardOp : cmpy_op_s {
   // Generation-3 row engine: uniform hop / U / eps, hop != 0, complete dn sector of <= 16 sites.
   int configure_eng(int n_dn, const int* s1, const int* s2, const double* eps) {
     if (!(uniform && eps_uniform) || hop0 == 0.0 || dn.num < 64) return CMPY_OK;
-    int rc = build_eng_host(eng.H, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, 32, false);
+    if (const char* e = getenv("CMPY_ENG_THREADS")) eng_threads = atoi(e) == 512 ? 512 : 1024;
+    int rc = build_eng_host(eng.H, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin,
+                            eng_threads / 32, false);
     if (rc || !eng.H.ok) return rc;
-    rc = raise_smem_limit(hub_eng_kernel<false, false, 1024>, smem_optin);
-    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, false, 1024>, smem_optin);
-    if (!rc) rc = raise_smem_limit(hub_eng_kernel<false, true, 1024>, smem_optin);
-    if (!rc) rc = raise_smem_limit(hub_eng_kernel<true, true, 1024>, smem_optin);
+    const int nb_lh = eng_nlh_bound(eng.H.C.nlh);
+    rc = nb_lh == 1 ? raise_eng_limits<1>() : nb_lh == 2 ? raise_eng_limits<2>() : raise_eng_limits<4>();
     if (rc) return rc;
     int nb = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_eng_kernel<true, true, 1024>, 1024, eng.H.smem));
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_eng_kernel<true, true, 1024, 4>, 1024, eng.H.smem));
     if (nb < 1) return CMPY_OK;
     CU_CHECK(cudaMalloc(&eng.d_dh_cm, sizeof(uint16_t) * eng.H.dh_cm.size()));
+    CU_CHECK(cudaMalloc(&eng.d_dl_q, sizeof(uint16_t) * eng.H.dl_q.size()));
+    CU_CHECK(cudaMemcpy(eng.d_dl_q, eng.H.dl_q.data(), sizeof(uint16_t) * eng.H.dl_q.size(), cudaMemcpyHostToDevice));
     CU_CHECK(cudaMalloc(&eng.d_lh_lane, sizeof(uint32_t) * eng.H.lh_lane.size()));
     CU_CHECK(cudaMemcpy(eng.d_dh_cm, eng.H.dh_cm.data(), sizeof(uint16_t) * eng.H.dh_cm.size(), cudaMemcpyHostToDevice));
     CU_CHECK(cudaMemcpy(eng.d_lh_lane, eng.H.lh_lane.data(), sizeof(uint32_t) * eng.H.lh_lane.size(), cudaMemcpyHostToDevice));

@@ -27,24 +27,23 @@ extern "C" int eng_emu_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   const eng_addr xs_a = (eng_addr)(uintptr_t)xs, ydelta = (eng_addr)xs_total * 8u;
   EngLane ln;
   ln.dh_cm = T.dh_cm.data();
-  ln.lh_lane = T.lh_lane.data();
+  ln.dl_of_q = T.dl_q.data();
+  ln.lh_lane = reinterpret_cast<const uint4*>(T.lh_lane.data());
   // staging (the cp.async loop of the kernel)
   std::vector<int> hit(C.xs_elems, 0);
   for (int warp = 0; warp < nwarps; ++warp)
     for (int it = C.sptr[warp]; it < C.sptr[warp + 1]; ++it) {
       const uint32_t ts = C.task_s[it];
-      const int sA = (int)(ts & 0xffffu), sB = sA + (int)(ts >> 16);
-      for (int s = sA; s < sB; ++s) {
-        const uint32_t w = C.seg_nat[s];
-        const int sk = C.S[w >> 28];
+      const int k = (int)(ts & 15u), jA = (int)((ts >> 8) & 255u), jB = jA + (int)((ts >> 16) & 255u);
+      const int sk = C.S[k];
+      for (int jj = jA; jj < jB; ++jj)
         for (int lane = 0; lane < 32; ++lane)
           for (int t = 0; t < 3; ++t)
             if (lane + 32 * t < sk) {
-              const int slot = (int)(w & 0x3fffu) + lane + 32 * t;
-              xs[slot] = x_row[((w >> 14) & 0x3fffu) + lane + 32 * t];
+              const int slot = (C.xb8[k] + jj * C.P8[k]) / 8 + lane + 32 * t;
+              xs[slot] = x_row[C.goff_cm[C.hoff[k] + jj] + lane + 32 * t];
               hit[slot] += 1;
             }
-      }
     }
   int staged = 0;
   for (int v : hit) { if (v > 1) return -2; staged += v; }
@@ -52,8 +51,17 @@ extern "C" int eng_emu_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   const double inv_hop = 1.0 / hop0;
   double e_dn_const = T.e_dn_const;
   const double eu_s = (e_up + e_dn_const) * inv_hop, u0_s = u0 * inv_hop;
+  std::vector<double> dg(ENG_MAX_Q + ENG_MAX_SEG, 0.0);
+  for (int i = 0; i < 1024; ++i) eng_fill_diag(C, ln, dg.data(), i, ups, eu_s, u0_s);
+  const eng_addr dg_a = (eng_addr)(uintptr_t)dg.data();
   for (int warp = 0; warp < nwarps; ++warp)
-    for (int lane = 0; lane < 32; ++lane) eng_run_a(C, ln, warp, xs_a, ydelta, ups, eu_s, u0_s, lane);
+    for (int lane = 0; lane < 32; ++lane) {
+      switch (eng_nlh_bound(C.nlh)) {
+        case 1: eng_run_a<1>(C, ln, warp, xs_a, ydelta, dg_a, lane); break;
+        case 2: eng_run_a<2>(C, ln, warp, xs_a, ydelta, dg_a, lane); break;
+        default: eng_run_a<4>(C, ln, warp, xs_a, ydelta, dg_a, lane); break;
+      }
+    }
   EngEpi E;
   E.xr = x_row; E.yr = y_row; E.hop0 = hop0; E.accumulate = accumulate; E.cu = 0;
   E.up_off = nullptr; E.up_coef = nullptr; E.s1 = 1.0; E.s2 = 0.0; E.has_prev = false;
