@@ -334,7 +334,7 @@ def l2_to_sm_roofline(workload, ms_per_step):
 # our arm
 # ---------------------------------------------------------------------------------------
 
-def parity_check(workload, hamop, x, y, world, dev):
+def parity_check(workload, x, y, world, dev, hamop):
     """Outside the timed region: rows of y = H x of the benchmarked operator against the C oracle
     (oracle/hv_oracle.c).  N = 1: 32-row blocks at the start, middle and end of the sector; N > 1:
     the same for rank 0's slab (x of the other ranks is regenerated from their seeds)."""
@@ -344,13 +344,9 @@ def parity_check(workload, hamop, x, y, world, dev):
     orc = build_port(workload)
     nd = len(orc.dn)
     if world == 1:
-        hamop.apply(x, out=y)
-        torch.cuda.synchronize()
         xf = x.cpu().numpy()
         r_lo, r_hi = 0, len(orc.up)
-    else:
-        hamop.apply_local(x, out=y)
-        torch.cuda.synchronize()
+    else:   # (y was computed collectively by the caller; only rank 0 gets here)
         parts = []
         for r in range(world):
             a, b = hamop.plan.rows(r)
@@ -514,11 +510,14 @@ def run_ours(args):
 
     # ---- parity of THIS configuration against the C oracle, outside the timed region ---------
     parity = None
-    if rank == 0 and not args.no_parity:
-        try:
-            parity = parity_check(args.workload, hamop, x, y, world, dev)
-        except Exception as exc:
-            parity = {"error": repr(exc)}
+    if not args.no_parity:
+        step()                     # collective on every rank: y = (H x)_local of the timed configuration
+        torch.cuda.synchronize()
+        if rank == 0:
+            try:
+                parity = parity_check(args.workload, x, y, world, dev, hamop)
+            except Exception as exc:
+                parity = {"error": repr(exc)}
     phases = None
     if world > 1 and getattr(hamop, "exchange", "") == "peer":
         try:

@@ -74,6 +74,14 @@ SIGNATURES = {
                                              POINTER(_p), c_int, c_int, c_int, _p]),
     "cmpy_transpose_pull_acc": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                         POINTER(_p), _p]),
+    "cmpy_dist_ctl_bytes": (c_int, []),
+    "cmpy_dist_create": (c_int, [_p, _p, c_int, c_int, POINTER(_p), POINTER(_p), POINTER(_p), POINTER(_p)]),
+    "cmpy_dist_destroy": (c_int, [_p]),
+    "cmpy_hv_apply_sharded": (c_int, [_p, _p, _p, c_int, _p]),
+    "cmpy_dist_allreduce_sum": (c_int, [_p, _p, _p, _p]),
+    "cmpy_dist_barrier": (c_int, [_p, _p]),
+    "cmpy_lanczos_sharded": (c_int, [_p, _p, _p, c_int, c_double, c_int, POINTER(c_double), POINTER(c_double),
+                                     POINTER(c_int), POINTER(c_double), _p]),
 }
 
 

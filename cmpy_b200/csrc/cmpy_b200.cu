@@ -12,6 +12,7 @@
 #include "greens.cuh"
 #include "heisenberg.cuh"
 #include "peer.cuh"
+#include "dist.cuh"
 
 #define API extern "C" __attribute__((visibility("default")))
 
@@ -499,4 +500,41 @@ API int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn,
   peer_transpose_kernel<true, 32><<<g, 256, 0, as_stream(stream)>>>(d_y_slab, nrows, num_dn, row0, ld_t, pt);
   KERNEL_CHECK();
   return CMPY_OK;
+}
+
+// ---- sharded H.v / sharded Lanczos as single C calls (dist.cuh) ----------------------------------
+API int cmpy_dist_ctl_bytes(void) { return (int)((sizeof(DistCtl) + 255) & ~(size_t)255); }
+
+API int cmpy_dist_create(cmpy_op_t op_main, cmpy_op_t op_t, int world, int rank, void* const* h_peer_xt,
+                         void* const* h_peer_yt, void* const* h_peer_ctl, cmpy_dist_t* out) {
+  return dist_create_impl(op_main, op_t, world, rank, h_peer_xt, h_peer_yt, h_peer_ctl, out);
+}
+
+API int cmpy_dist_destroy(cmpy_dist_t d) {
+  delete d;
+  return CMPY_OK;
+}
+
+API int cmpy_hv_apply_sharded(cmpy_dist_t d, const double* d_x_slab, double* d_y_slab, int accumulate,
+                              void* stream) {
+  ARG_CHECK(d && d_x_slab && d_y_slab, "null argument");
+  return d->apply(d_x_slab, d_y_slab, accumulate ? 1 : 0, false, as_stream(stream));
+}
+
+API int cmpy_dist_allreduce_sum(cmpy_dist_t d, const double* d_in2, double* d_out2, void* stream) {
+  ARG_CHECK(d && d_in2 && d_out2, "null argument");
+  CU_CHECK(cudaMemcpyAsync(d->d_part, d_in2, sizeof(double) * DIST_NVAL, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return d->allreduce(0, d_out2, as_stream(stream));
+}
+
+API int cmpy_dist_barrier(cmpy_dist_t d, void* stream) {
+  ARG_CHECK(d, "null argument");
+  return d->barrier(as_stream(stream));
+}
+
+API int cmpy_lanczos_sharded(cmpy_dist_t d, double* d_r_slab, double* d_w_slab, int maxit, double tol,
+                             int check_every, double* h_alpha, double* h_beta, int* h_nit, double* h_e0,
+                             void* stream) {
+  return dist_lanczos_impl(d, d_r_slab, d_w_slab, maxit, tol, check_every, h_alpha, h_beta, h_nit, h_e0,
+                           as_stream(stream));
 }

@@ -33,6 +33,8 @@ struct HubParams {
   i64 row0, nrows;    // slab of rows handled by this launch (x, y point at the slab)
   int with_up;        // include up hops (needs the whole vector: row0 == 0, nrows == num_up)
   int accumulate;     // y += instead of y =
+  const double* acc_scale;  // device {c1, c2} (or null): y = c1 * (H x) + c2 * y  (row engine only; used by the
+                            // sharded Lanczos recurrence, cmpy/exactdiag.py:324-347 in the unnormalised basis)
   const double* x;
   double* y;
   LzCtx lz;

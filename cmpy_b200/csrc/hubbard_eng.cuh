@@ -259,6 +259,7 @@ struct EngEpi {
   double* yr;           // row of y
   double hop0;
   int accumulate;
+  double c1, c2;        // scaled accumulation y = c1 * a + c2 * y (accumulate == 2)
   int cu;               // up-hop gathers of this row
   const i64* up_off;    // [cu] element offset of the source row relative to xr (shared memory)
   const double* up_coef;
@@ -340,7 +341,7 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
           dot += (E.s1 * eng_ld(own + 256u * t)) * w;
           *yp = w;
         } else {
-          *yp = E.accumulate ? *yp + a : a;
+          *yp = E.accumulate == 2 ? E.c1 * a + E.c2 * *yp : E.accumulate ? *yp + a : a;
         }
       }
     }
@@ -399,6 +400,8 @@ __global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ 
   const double u0_s = p.u0 * inv_hop;
   EngEpi E;
   E.hop0 = p.hop0; E.accumulate = p.accumulate; E.s1 = s1; E.s2 = s2; E.has_prev = has_prev;
+  E.c1 = 1.0; E.c2 = 0.0;
+  if (p.acc_scale) { E.accumulate = 2; E.c1 = p.acc_scale[0]; E.c2 = p.acc_scale[1]; }
   E.up_off = s_up_off; E.up_coef = s_up_coef; E.cu = 0;
   const uint32_t dst_l = xs_a + (uint32_t)lane * 8u;
   __syncthreads();

@@ -86,7 +86,7 @@ struct HubbardOp : cmpy_op_s {
     p.hop = d_hop; p.u = d_u; p.num_sites = num_sites;
     p.u0 = u0; p.hop0 = hop0;
     p.row0 = 0; p.nrows = up.num; p.with_up = 1; p.accumulate = 0;
-    p.x = nullptr; p.y = nullptr;
+    p.x = nullptr; p.y = nullptr; p.acc_scale = nullptr;
     p.lz.enabled = 0; p.lz.iter = nullptr; p.lz.beta = nullptr; p.lz.alpha = nullptr;
     p.lz.partials = d_partials; p.lz.ticket = d_ticket;
     return p;
@@ -144,6 +144,9 @@ struct HubbardOp : cmpy_op_s {
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant (engine 2) not available for this call");
     if (use_variant == 11 && !(eng.ok && UNI))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row-engine variant not available for this sector");
+    if (p.acc_scale && !(eng.ok && UNI && !LZ && (use_variant == 0 || use_variant == 11)))
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "scaled accumulation needs the row engine");
+    if (p.acc_scale) return launch_eng<LZ>(p, st);
     if (use_variant == 11 || (use_variant == 0 && eng.ok && UNI && (!p.with_up || eng_full)))
       return launch_eng<LZ>(p, st);
     if (use_variant == 10) return launch_long(p, st, lng2, 2);
@@ -492,10 +495,10 @@ struct HubbardOp : cmpy_op_s {
   }
 
   int apply_slab(const double* x, double* y, i64 row0, i64 nrows, int with_up, int accumulate,
-                 const LzCtx& lz, cudaStream_t st) {
+                 const LzCtx& lz, cudaStream_t st, const double* acc_scale = nullptr) {
     HubParams p = base_params();
     p.x = x; p.y = y; p.row0 = row0; p.nrows = nrows; p.with_up = with_up;
-    p.accumulate = accumulate;
+    p.accumulate = accumulate; p.acc_scale = acc_scale;
     if (lz.enabled) {
       p.lz = lz; p.lz.partials = d_partials; p.lz.ticket = d_ticket;
       return uniform ? launch<true, true>(p, variant, st) : launch<false, true>(p, variant, st);

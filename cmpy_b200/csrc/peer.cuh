@@ -36,7 +36,8 @@ __device__ __forceinline__ int peer_owner(const PeerTable& t, i64 c) {
 template <bool PULL, int PEER_TR>
 __global__ void __launch_bounds__(256) peer_transpose_kernel(double* __restrict__ loc, i64 nrows,
                                                              i64 nd, i64 row0, i64 ld_t,
-                                                             PeerTable pt) {
+                                                             PeerTable pt, const double* __restrict__ scale = nullptr) {
+  const double sc = (PULL && scale) ? scale[0] : 1.0;   // pull: y += sc * YT^T (device scalar of the sharded Lanczos)
   __shared__ double tile[32][PEER_TR + 1];  // [column][row]
   const i64 tiles_c = (nd + 31) / 32, tiles_r = (nrows + PEER_TR - 1) / PEER_TR;
   const i64 ntiles = tiles_c * tiles_r;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) peer_transpose_kernel(double* __restrict_
 #pragma unroll 4
       for (int k = ty; k < PEER_TR; k += 8) {
         const i64 r = r0 + k, c = c0 + tx;
-        if (r < nrows && c < nd) loc[r * nd + c] += tile[tx][k];
+        if (r < nrows && c < nd) loc[r * nd + c] += sc * tile[tx][k];
       }
     }
   }

@@ -144,6 +144,7 @@ class ShardedHubbardOperator:
                                           zeros, zeros, spec["sign_width"])
             backend = CudaBackend(op_main, op_t)
         self.backend = backend
+        self._cdist = None
         self.plan = ShardPlan(len(up_states), len(dn_states), self.world, self.rank)
         size = self.plan.num_up * self.plan.num_dn
         self.shape = (size, size)
@@ -179,6 +180,7 @@ class ShardedHubbardOperator:
     def _init_peer(self):
         """XT / YT slabs in symmetric memory + the peer pointer tables of the transpose kernels."""
         import ctypes
+        import os
 
         import torch.distributed._symmetric_memory as symm
 
@@ -213,9 +215,39 @@ class ShardedHubbardOperator:
         # CMPY_PULL_PARTS=k (opt-in, not yet measured): the up pass runs in k chunks of the owned
         # dn-columns and the pull of chunk i overlaps the up pass of chunk i + 1
         self._pull_parts = max(1, int(os.environ.get("CMPY_PULL_PARTS", "1")))
+        # the same choreography as ONE C call (cmpy_hv_apply_sharded): control block in symmetric memory
+        # for the library's own barrier / all-reduce kernels
+        self._cdist = None
+        if os.environ.get("CMPY_DIST_PYTHON", "") != "1":
+            L = _lib.lib()
+            nctl = max(int(L.cmpy_dist_ctl_bytes()) // 8, 1)
+            self._ctl_sym = symm.empty(nctl, dtype=torch.float64, device=dev)
+            self._ctl_sym.zero_()
+            self._h_ctl = symm.rendezvous(self._ctl_sym, group)
+            torch.cuda.synchronize()
+            self._h_ctl.barrier(channel=0)     # every control block is zero before the first handshake
+            peer_ctl = (ctypes.c_void_p * self.world)(*[int(a) for a in self._h_ctl.buffer_ptrs])
+            handle = ctypes.c_void_p()
+            _lib.check(L.cmpy_dist_create(self.backend.op_main.handle, self.backend.op_t.handle, self.world,
+                                          self.rank, self._peer_xt, self._peer_yt, peer_ctl, ctypes.byref(handle)),
+                       "cmpy_dist_create")
+            self._cdist = handle
+
+    def __del__(self):
+        h, self._cdist = getattr(self, "_cdist", None), None
+        if h:
+            try:
+                _lib.lib().cmpy_dist_destroy(h)
+            except Exception:
+                pass
 
     def _apply_local_peer(self, x_local, out, accumulate=False):
         torch = _lib.require_cuda()
+        if self._cdist is not None and not self._dn_first and self._pull_parts == 1:
+            _lib.check(_lib.lib().cmpy_hv_apply_sharded(self._cdist, _lib.ptr(x_local), _lib.ptr(out),
+                                                        int(bool(accumulate)), _lib.stream_ptr()),
+                       "cmpy_hv_apply_sharded")
+            return out
         p, be, L = self.plan, self.backend, _lib.lib()
         r0, _ = p.rows()
         c0, _ = p.cols()
@@ -420,6 +452,10 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
     import torch
     from scipy.linalg import eigvalsh_tridiagonal
 
+    if (getattr(op, "_cdist", None) is not None and callback is None and not want_vector and resid_tol <= 0):
+        res = _lanczos_sharded_c(op, v0_local, maxit, tol, check_every, seed)
+        if res is not None:
+            return res
     dist = op.dist
     multi = dist.is_initialized() and op.world > 1
 
@@ -519,6 +555,37 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
     return e0, ah, bh, nit, converged, psi
 
 
+def _lanczos_sharded_c(op, v0_local, maxit, tol, check_every, seed):
+    """The recurrence of ``lanczos_sharded`` as one C call (``cmpy_lanczos_sharded``: fused device kernels,
+    device-side all-reduces over the control blocks).  ``None`` when the operator has no row engine."""
+    import ctypes
+
+    torch = _lib.require_cuda()
+    n = op.local_size
+    dev = _lib.device()
+    if v0_local is None:
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(seed) + 7919 * op.rank)
+        r = torch.randn(max(n, 1), dtype=torch.float64, device=dev, generator=g)
+    else:
+        r = v0_local.clone()
+    w = torch.empty_like(r)
+    cap = int(maxit) + int(check_every) + 4
+    alpha = np.zeros(cap, dtype=np.float64)
+    beta = np.zeros(cap + 1, dtype=np.float64)
+    nit, e0 = ctypes.c_int(0), ctypes.c_double(0.0)
+    rc = _lib.lib().cmpy_lanczos_sharded(
+        op._cdist, _lib.ptr(r), _lib.ptr(w), int(maxit), float(tol), int(check_every),
+        alpha.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        ctypes.byref(nit), ctypes.byref(e0), _lib.stream_ptr())
+    if rc == _lib.CMPY_ERR_UNSUPPORTED:
+        return None
+    if rc not in (_lib.CMPY_OK, _lib.CMPY_ERR_NOT_CONVERGED):
+        _lib.check(rc, "cmpy_lanczos_sharded")
+    m = nit.value
+    return e0.value, alpha[:m].copy(), beta[1:m + 1].copy(), m, rc == _lib.CMPY_OK
+
+
 def gf_continued_fraction_sharded(model, z, pos=0, n_up=None, n_dn=None, num_coeffs=600, tol=1e-12,
                                   group=None, return_info=False):
     """Zero-temperature G_{pos,DN}(z) on an up-string-sharded sector: sharded Lanczos ground state,
@@ -551,7 +618,9 @@ def gf_continued_fraction_sharded(model, z, pos=0, n_up=None, n_dn=None, num_coe
             continue
         sec_t = Sector(up_slab, np.asarray(basis.get_states(nd_t)), n_up, nd_t, L)
         phi = cls(sec_slab, sec_t, pos=pos, sigma=DN).apply(psi)
-        nrm = torch.dot(phi, phi)
+        nrm = torch.zeros((), dtype=phi.dtype, device=phi.device)
+        for i0 in range(0, phi.numel(), 1 << 30):   # cuBLAS dot is limited to 2^31 - 1 elements
+            nrm += torch.dot(phi[i0:i0 + (1 << 30)], phi[i0:i0 + (1 << 30)])
         if op_world(group) > 1:
             import torch.distributed as dist
 

@@ -223,6 +223,39 @@ int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int
                             int64_t ld_t, int world, const int64_t* h_col_bounds,
                             void* const* h_peer_ptrs, void* stream);
 
+/* ---- the sharded H.v and the sharded Lanczos recurrence as single C calls ----
+ * One process per GPU (last row / 8(e)).  The caller owns three symmetric
+ * (peer-mapped) allocations per rank -- the dn-major slabs XT and YT (max_q ncols_q * num_up doubles) and a
+ * zero-initialised control block of cmpy_dist_ctl_bytes() bytes -- and hands over, for each of them, the
+ * table of device pointers through which THIS process addresses every rank's copy (how they are mapped is
+ * the caller's business: torch.distributed._symmetric_memory, cuMem* fabric handles or cudaIpc*).
+ * op_main: Hubbard operator of the sector (rows = up strings); op_t: the operator with the roles of the
+ * species swapped and eps = u = 0 (its dn hops are the up hops of H).  Rows / columns are partitioned as
+ * [floor(n k / world), floor(n (k + 1) / world)).  Cross-rank ordering uses the library's own barrier
+ * kernel over the control blocks; every rank must issue the same sequence of cmpy_dist_* calls.
+ * No reference counterpart: cmpy has no distributed path; layout cmpy/operators.py:33-90, Lanczos
+ * recurrence cmpy/exactdiag.py:324-347. */
+typedef struct cmpy_dist_s* cmpy_dist_t;
+int cmpy_dist_ctl_bytes(void);
+int cmpy_dist_create(cmpy_op_t op_main, cmpy_op_t op_t, int world, int rank, void* const* h_peer_xt,
+                     void* const* h_peer_yt, void* const* h_peer_ctl, cmpy_dist_t* out);
+int cmpy_dist_destroy(cmpy_dist_t d);
+/* y_slab = (H x)_slab (accumulate: y_slab += ...): barrier, push || local dn pass, barrier, up pass on the
+ * dn-major slab, barrier, pull-accumulate. */
+int cmpy_hv_apply_sharded(cmpy_dist_t d, const double* d_x_slab, double* d_y_slab, int accumulate,
+                          void* stream);
+/* out[0..1] = sum over ranks of in[0..1] (fixed rank order, bit-identical on every rank). */
+int cmpy_dist_allreduce_sum(cmpy_dist_t d, const double* d_in2, double* d_out2, void* stream);
+int cmpy_dist_barrier(cmpy_dist_t d, void* stream);
+/* Two-vector sharded Lanczos from the (unnormalised) start slab d_r_slab (overwritten; d_w_slab is the
+ * second slab).  h_alpha[maxit], h_beta[maxit + 1] (beta[0] = |r_0|); stops when the lowest Ritz value moves
+ * by less than tol between two checks (every check_every iterations) or at a breakdown.  Returns CMPY_OK or
+ * CMPY_ERR_NOT_CONVERGED; needs the row engine (uniform model, rows of at most 16 sites), otherwise
+ * CMPY_ERR_UNSUPPORTED. */
+int cmpy_lanczos_sharded(cmpy_dist_t d, double* d_r_slab, double* d_w_slab, int maxit, double tol,
+                         int check_every, double* h_alpha, double* h_beta, int* h_nit, double* h_e0,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ extern "C" int eng_emu_row(int num_sites, int n_dn, int nbonds, const int* s1, c
       }
     }
   EngEpi E;
-  E.xr = x_row; E.yr = y_row; E.hop0 = hop0; E.accumulate = accumulate; E.cu = 0;
+  E.xr = x_row; E.yr = y_row; E.hop0 = hop0; E.accumulate = accumulate; E.cu = 0; E.c1 = 1.0; E.c2 = 0.0;
   E.up_off = nullptr; E.up_coef = nullptr; E.s1 = 1.0; E.s2 = 0.0; E.has_prev = false;
   double dot = 0.0;
   for (int warp = 0; warp < nwarps; ++warp)

@@ -113,6 +113,87 @@ def test_sharded_sequence_with_virtual_ranks(L, nu_f, nd_f, nbfn, world):
     assert np.abs(got - full).max() / np.abs(ref).max() < 1e-12
 
 
+@pytest.mark.parametrize("L,nu_f,nd_f,nbfn", [
+    (8, 4, 4, lambda: orc.chain_neighbors(8)),
+    (10, 5, 5, lambda: orc.square_neighbors(2, 5)),
+    (12, 6, 6, lambda: orc.square_neighbors(4, 3)),
+])
+def test_c_dist_calls_world1(L, nu_f, nd_f, nbfn):
+    """cmpy_dist_create / cmpy_hv_apply_sharded / cmpy_dist_allreduce_sum / cmpy_lanczos_sharded with a
+    world of one rank (peer tables = local buffers): the C choreography, the library's own barrier and
+    all-reduce kernels, the scaled accumulation of the row engine and of the pull kernel, and the
+    device-scalar Lanczos driver -- against the oracle and the single-GPU fused Lanczos."""
+    import torch
+    from cmpy_b200 import _lib
+    from cmpy_b200.exactdiag import lanczos_run
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.operators import SectorHamiltonOperator
+
+    lib = _lib.lib()
+    nb = nbfn()
+    kw = dict(inter=4.0, mu=2.0, hop=1.0)
+    model = HubbardModel(L, nb, **kw)
+    spec = model._operator_spec()
+    up, dn = orc.enumerate_states(L, nu_f), orc.enumerate_states(L, nd_f)
+    nu, nd = len(up), len(dn)
+    op_main = SectorHamiltonOperator(L, up, dn, spec["bonds"], spec["hops"], spec["eps"], spec["u"],
+                                     spec["sign_width"])
+    zeros = np.zeros(L)
+    op_t = SectorHamiltonOperator(L, dn, up, spec["bonds"], spec["hops"], zeros, zeros, spec["sign_width"])
+    xt = torch.zeros(nu * nd, dtype=torch.float64, device="cuda")
+    yt = torch.zeros_like(xt)
+    ctl = torch.zeros(int(lib.cmpy_dist_ctl_bytes()) // 8, dtype=torch.float64, device="cuda")
+    one = lambda t: (ctypes.c_void_p * 1)(t.data_ptr())
+    handle = ctypes.c_void_p()
+    _lib.check(lib.cmpy_dist_create(op_main.handle, op_t.handle, 1, 0, one(xt), one(yt), one(ctl),
+                                    ctypes.byref(handle)))
+    try:
+        xh = np.random.default_rng(9).standard_normal(nu * nd)
+        x = torch.from_numpy(xh).cuda()
+        y = torch.full_like(x, float("nan"))
+        _lib.check(lib.cmpy_hv_apply_sharded(handle, _lib.ptr(x), _lib.ptr(y), 0, _lib.stream_ptr()))
+        ref = orc.hubbard_matvec_free(up, dn, nb, kw["inter"], -kw["mu"], kw["hop"], xh, width=L)
+        assert np.abs(y.cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-12
+        y2 = x.clone()
+        _lib.check(lib.cmpy_hv_apply_sharded(handle, _lib.ptr(x), _lib.ptr(y2), 1, _lib.stream_ptr()))
+        assert np.abs(y2.cpu().numpy() - (ref + xh)).max() / np.abs(ref).max() < 1e-12
+        part = torch.tensor([1.25, -3.5], dtype=torch.float64, device="cuda")
+        tot = torch.zeros(2, dtype=torch.float64, device="cuda")
+        for _ in range(3):   # both slot parities
+            _lib.check(lib.cmpy_dist_allreduce_sum(handle, _lib.ptr(part), _lib.ptr(tot), _lib.stream_ptr()))
+            _lib.check(lib.cmpy_dist_barrier(handle, _lib.stream_ptr()))
+        assert tot.cpu().tolist() == [1.25, -3.5]
+        # sharded Lanczos driver == single-GPU fused Lanczos (same start vector), coefficient by coefficient
+        h = model.hamilton_operator(nu_f, nd_f)
+        res = lanczos_run(h, x, maxit=60, tol=0.0, check_every=60)
+        r, w = x.clone(), torch.empty_like(x)
+        alpha = np.zeros(80); beta = np.zeros(81)
+        nit, e0 = ctypes.c_int(0), ctypes.c_double(0.0)
+        rc = lib.cmpy_lanczos_sharded(handle, _lib.ptr(r), _lib.ptr(w), 60, 0.0, 60,
+                                      alpha.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      ctypes.byref(nit), ctypes.byref(e0), _lib.stream_ptr())
+        if rc == _lib.CMPY_ERR_UNSUPPORTED:   # sector outside the row engine (e.g. more than 4 LH bonds):
+            assert b"row engine" in lib.cmpy_last_error()   # the Python recurrence is the documented fallback
+            return
+        assert rc in (_lib.CMPY_OK, _lib.CMPY_ERR_NOT_CONVERGED), lib.cmpy_last_error()
+        m = min(nit.value, res.nit, 40)
+        assert m >= 20
+        assert np.allclose(alpha[:m], res.alpha[:m], rtol=0, atol=1e-9 * max(1.0, np.abs(res.alpha).max()))
+        assert np.allclose(beta[:m + 1], res.beta[:m + 1], rtol=0, atol=1e-9 * max(1.0, np.abs(res.beta).max()))
+        # and converges to the ground-state energy of the dense / sparse reference
+        r = x.clone()
+        rc = lib.cmpy_lanczos_sharded(handle, _lib.ptr(r), _lib.ptr(w), 70, 1e-11, 10,
+                                      alpha.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      ctypes.byref(nit), ctypes.byref(e0), _lib.stream_ptr())
+        ref_run = lanczos_run(h, x, maxit=400, tol=1e-12)
+        if rc == _lib.CMPY_OK:
+            assert abs(e0.value - ref_run.e0) < 1e-9
+    finally:
+        lib.cmpy_dist_destroy(handle)
+
+
 def test_c_example_runs():
     """examples/e0_from_c.c on the GPU: E0 of the 8-site chain from a plain-C client of the ABI."""
     import subprocess

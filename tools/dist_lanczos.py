@@ -52,7 +52,8 @@ def cb(nit, e):
     if rank == 0:
         print(f"  it {nit:4d}  E0 = {e:.12f}  ({time.time() - t1:.1f} s)", flush=True)
 dist.barrier(); torch.cuda.synchronize(); t1 = time.time()
-e0, al, be, nit, conv = lanczos_sharded(op, maxit=maxit, tol=1e-10, check_every=10, callback=cb)
+verbose = os.environ.get("DIST_LANCZOS_VERBOSE", "0") == "1"   # the callback forces the Python recurrence
+e0, al, be, nit, conv = lanczos_sharded(op, maxit=maxit, tol=1e-10, check_every=10, callback=cb if verbose else None)
 torch.cuda.synchronize(); dist.barrier()
 t_lz = time.time() - t1
 mem = torch.cuda.max_memory_allocated() / 1e9
@@ -61,6 +62,7 @@ if rank == 0:
     out = dict(workload=wl, L=L, U=U, dim=dim, n_gpus=world, exchange=op.exchange, build_s=t_build,
                hv_ms=hv_ms, hv_algorithmic_gbs_per_gpu=16.0 * dim / world / (hv_ms * 1e-3) / 1e9,
                nvlink_out_gbs_per_gpu=p.bytes_out_per_hv() / (hv_ms * 1e-3) / 1e9,
+               lanczos_path=("python" if (verbose or getattr(op, "_cdist", None) is None) else "c (cmpy_lanczos_sharded)"),
                lanczos_s=t_lz, iterations=nit, converged=bool(conv), e0=e0,
                ms_per_iteration=1e3 * t_lz / max(nit, 1), max_mem_gb=mem, phases_ms=phases)
     if U == 0.0:  # free fermions: E0 = 2 * sum of the n lowest levels of the hopping matrix (mu = 0)
