@@ -549,6 +549,19 @@ def run_ours(args):
                                   "converged": bool(r14.converged), "dim": h14.shape[0]}
             del h14
 
+    if world > 1 and not args.no_lanczos:
+        from cmpy_b200.dist import lanczos_sharded
+
+        lanczos_sharded(hamop, maxit=10, tol=1e-10, check_every=10)      # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        e0s, _, _, nits, convs = lanczos_sharded(hamop, maxit=1000, tol=1e-10, check_every=10)
+        barrier()
+        lanczos = {"seconds": time.perf_counter() - t0, "iterations": int(nits), "e0": float(e0s),
+                   "converged": bool(convs), "tol": 1e-10,
+                   "path": ("cmpy_lanczos_sharded (C call, device-side all-reduces)"
+                            if getattr(hamop, "_cdist", None) is not None else "python recurrence")}
+
     clocks = sampler.stop() if sampler is not None else None
 
     if rank == 0:

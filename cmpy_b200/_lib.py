@@ -70,8 +70,6 @@ SIGNATURES = {
                                     POINTER(_p), _p]),
     "cmpy_transpose_push_capped": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                            POINTER(_p), c_int, _p]),
-    "cmpy_transpose_pull_acc_part": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
-                                             POINTER(_p), c_int, c_int, c_int, _p]),
     "cmpy_transpose_pull_acc": (c_int, [_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(c_int64),
                                         POINTER(_p), _p]),
     "cmpy_dist_ctl_bytes": (c_int, []),

@@ -464,28 +464,6 @@ API int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_
   return CMPY_OK;
 }
 
-API int cmpy_transpose_pull_acc_part(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
-                                     int64_t ld_t, int world, const int64_t* h_col_bounds,
-                                     void* const* h_peer_ptrs, int part, int nparts, int max_ctas,
-                                     void* stream) {
-  ARG_CHECK(d_y_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
-  ARG_CHECK(nparts >= 1 && part >= 0 && part < nparts && max_ctas >= 0, "pull part: bad part");
-  PeerTable pt;
-  int rc = fill_peer_table(pt, world, h_col_bounds, h_peer_ptrs);
-  if (rc) return rc;
-  ARG_CHECK(pt.cb[0] == 0 && pt.cb[world] == num_dn, "peer transpose: bounds must cover the columns");
-  PeerPart pp;
-  peer_part_fill(pp, pt, part, nparts);
-  const i64 vtot = pp.vstart[world];
-  if (nrows == 0 || vtot == 0) return CMPY_OK;
-  const i64 ntiles = ((nrows + 31) / 32) * ((vtot + 31) / 32);
-  int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-  if (max_ctas > 0 && g > max_ctas) g = max_ctas;
-  peer_pull_part_kernel<32><<<g, 256, 0, as_stream(stream)>>>(d_y_slab, nrows, num_dn, row0, ld_t, pt, pp);
-  KERNEL_CHECK();
-  return CMPY_OK;
-}
-
 API int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                                 int64_t ld_t, int world, const int64_t* h_col_bounds,
                                 void* const* h_peer_ptrs, void* stream) {

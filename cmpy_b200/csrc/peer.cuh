@@ -86,75 +86,3 @@ __global__ void __launch_bounds__(256) peer_transpose_kernel(double* __restrict_
     }
   }
 }
-
-// ---------------------------------------------------------------------------------
-// Chunked second half of the sharded H.v (opt-in, CMPY_PULL_PARTS > 1 in cmpy_b200/dist.py):
-// every rank runs its up pass in `nparts` chunks of the dn-columns it owns; the pull of chunk k
-// (this kernel, on a side stream and on the SMs the capped up-pass grid leaves free) overlaps the
-// up pass of chunk k + 1.  Part `part` of owner q is the column range
-//   [cb[q] + n_q * part / nparts, cb[q] + n_q * (part + 1) / nparts),   n_q = cb[q+1] - cb[q],
-// (integer division; the host uses the same formula for the up-pass chunks).  The kernel walks the
-// concatenation of these ranges ("virtual columns") in tiles of 32, otherwise like the pull above:
-//   y[r, c] += YT_q[c - cb[q], row0 + r].
-struct PeerPart {
-  i64 lo[PEER_MAX];       // first column of the part of owner q
-  i64 vstart[PEER_MAX + 1];  // prefix sums of the part lengths
-};
-
-__host__ __device__ __forceinline__ i64 peer_part_column(const PeerTable& t, const PeerPart& pp, i64 v, int& q) {
-  q = 0;
-#pragma unroll 1
-  while (q + 1 < t.world && v >= pp.vstart[q + 1]) ++q;
-  return pp.lo[q] + (v - pp.vstart[q]);
-}
-
-// part `part` of `nparts` of every owner's column range (host side of cmpy_transpose_pull_acc_part)
-static inline void peer_part_fill(PeerPart& pp, const PeerTable& pt, int part, int nparts) {
-  pp.vstart[0] = 0;
-  for (int q = 0; q < pt.world; ++q) {
-    const i64 n = pt.cb[q + 1] - pt.cb[q];
-    const i64 lo = pt.cb[q] + n * part / nparts, hi = pt.cb[q] + n * (part + 1) / nparts;
-    pp.lo[q] = lo;
-    pp.vstart[q + 1] = pp.vstart[q] + (hi - lo);
-  }
-}
-
-template <int PEER_TR>
-__global__ void __launch_bounds__(256) peer_pull_part_kernel(double* __restrict__ loc, i64 nrows, i64 nd,
-                                                             i64 row0, i64 ld_t, PeerTable pt, PeerPart pp) {
-  __shared__ double tile[32][PEER_TR + 1];  // [virtual column][row]
-  const i64 vtot = pp.vstart[pt.world];
-  const i64 tiles_c = (vtot + 31) / 32, tiles_r = (nrows + PEER_TR - 1) / PEER_TR;
-  const i64 ntiles = tiles_c * tiles_r;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (i64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const i64 tr = t / tiles_c, tc = t - tr * tiles_c;
-    const i64 r0 = tr * PEER_TR, v0 = tc * 32;
-    __syncthreads();
-#pragma unroll
-    for (int k = ty; k < 32; k += 8) {
-      const i64 v = v0 + k;
-      if (v < vtot) {
-        int q;
-        const i64 c = peer_part_column(pt, pp, v, q);
-        const double* src = pt.base[q] + (c - pt.cb[q]) * ld_t + row0 + r0;
-#pragma unroll
-        for (int j = tx; j < PEER_TR; j += 32)
-          if (r0 + j < nrows) tile[k][j] = src[j];
-      }
-    }
-    __syncthreads();
-    {
-      const i64 v = v0 + tx;
-      if (v < vtot) {
-        int q;
-        const i64 c = peer_part_column(pt, pp, v, q);
-#pragma unroll 4
-        for (int k = ty; k < PEER_TR; k += 8) {
-          const i64 r = r0 + k;
-          if (r < nrows) loc[r * nd + c] += tile[tx][k];
-        }
-      }
-    }
-  }
-}

@@ -205,16 +205,6 @@ class ShardedHubbardOperator:
         import os
         self._sm_count = torch.cuda.get_device_properties(_lib.device()).multi_processor_count
         self._push_sms = int(os.environ.get("CMPY_PUSH_SMS", "32"))
-        # CMPY_PUSH_ORDER=dn_first (opt-in, not yet measured): enqueue the local dn pass first, on a
-        # high-priority stream, and cap the push grid at the CTAs that fit the reserved SMs.  With the
-        # default order the persistent push CTAs (8 per SM) are resident on every SM before the dn
-        # pass arrives, and a class-major CTA needs a whole SM's shared memory: at C5 only about 20 ms
-        # of the 54 ms push are hidden.
-        self._dn_first = os.environ.get("CMPY_PUSH_ORDER", "") == "dn_first"
-        self._hi = torch.cuda.Stream(priority=-1) if self._dn_first else None
-        # CMPY_PULL_PARTS=k (opt-in, not yet measured): the up pass runs in k chunks of the owned
-        # dn-columns and the pull of chunk i overlaps the up pass of chunk i + 1
-        self._pull_parts = max(1, int(os.environ.get("CMPY_PULL_PARTS", "1")))
         # the same choreography as ONE C call (cmpy_hv_apply_sharded): control block in symmetric memory
         # for the library's own barrier / all-reduce kernels
         self._cdist = None
@@ -243,7 +233,7 @@ class ShardedHubbardOperator:
 
     def _apply_local_peer(self, x_local, out, accumulate=False):
         torch = _lib.require_cuda()
-        if self._cdist is not None and not self._dn_first and self._pull_parts == 1:
+        if self._cdist is not None:
             _lib.check(_lib.lib().cmpy_hv_apply_sharded(self._cdist, _lib.ptr(x_local), _lib.ptr(out),
                                                         int(bool(accumulate)), _lib.stream_ptr()),
                        "cmpy_hv_apply_sharded")
@@ -255,22 +245,6 @@ class ShardedHubbardOperator:
         main = torch.cuda.current_stream()
         # every rank is done with the XT / YT slabs of the previous call
         self._h_xt.barrier(channel=0)
-        if self._dn_first and self.world > 1 and 0 < self._push_sms < self._sm_count:
-            ready = main.record_event()
-            self._hi.wait_event(ready)
-            with torch.cuda.stream(self._hi):
-                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, self._sm_count - self._push_sms),
-                           "cmpy_hubbard_set_grid_limit")
-                be.apply_rows(x_local, r0, nrows, out, accumulate=bool(accumulate))
-                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_main.handle, 0), "cmpy_hubbard_set_grid_limit")
-            self._side.wait_event(ready)
-            with torch.cuda.stream(self._side):
-                _lib.check(L.cmpy_transpose_push_capped(_lib.ptr(x_local), nrows, nd, r0, nu, self.world, self._cb,
-                                                        self._peer_xt, 6 * self._push_sms, _lib.stream_ptr()),
-                           "cmpy_transpose_push_capped")
-            main.wait_stream(self._hi)
-            main.wait_stream(self._side)
-            return self._apply_second_half(out, r0, c0, nrows, ncols, nu, nd)
         # push the transposed tiles into the owners' XT slabs (side stream) under the local
         # diagonal + dn-hop pass (main stream)
         self._side.wait_stream(main)
@@ -287,36 +261,7 @@ class ShardedHubbardOperator:
         main.wait_stream(self._side)
         return self._apply_second_half(out, r0, c0, nrows, ncols, nu, nd)
 
-    def _apply_second_half_chunked(self, out, r0, c0, nrows, ncols, nu, nd):
-        """Up pass in ``_pull_parts`` chunks; chunk i is pulled (side stream, capped grid) while
-        chunk i + 1 is computed (main stream, grid capped to leave SMs to the pull)."""
-        torch = _lib.require_cuda()
-        be, L = self.backend, _lib.lib()
-        parts = self._pull_parts
-        main, side = torch.cuda.current_stream(), self._side
-        self._h_xt.barrier(channel=0)          # all pushes have landed
-        reserve = self._push_sms if 0 < self._push_sms < self._sm_count else 0
-        for k in range(parts):
-            lo, hi = ncols * k // parts, ncols * (k + 1) // parts   # same split as the kernel's
-            if hi > lo:
-                limit = self._sm_count - reserve if (k > 0 and reserve) else 0
-                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_t.handle, limit), "cmpy_hubbard_set_grid_limit")
-                be.apply_rows_t(self._xt[lo * nu:], c0 + lo, hi - lo, self._yt[lo * nu:])
-                _lib.check(L.cmpy_hubbard_set_grid_limit(be.op_t.handle, 0), "cmpy_hubbard_set_grid_limit")
-            done = main.record_event()
-            side.wait_event(done)
-            with torch.cuda.stream(side):
-                self._h_yt.barrier(channel=1)  # chunk k of every YT slab is complete
-                _lib.check(L.cmpy_transpose_pull_acc_part(_lib.ptr(out), nrows, nd, r0, nu, self.world, self._cb,
-                                                          self._peer_yt, k, parts,
-                                                          6 * reserve if k + 1 < parts else 0,
-                                                          _lib.stream_ptr()), "cmpy_transpose_pull_acc_part")
-        main.wait_stream(side)
-        return out
-
     def _apply_second_half(self, out, r0, c0, nrows, ncols, nu, nd):
-        if self._pull_parts > 1 and self.world > 1:
-            return self._apply_second_half_chunked(out, r0, c0, nrows, ncols, nu, nd)
         be, L = self.backend, _lib.lib()
         self._h_xt.barrier(channel=0)          # all pushes have landed
         be.apply_rows_t(self._xt, c0, ncols, self._yt)   # up hops, row-local in the dn-major slab

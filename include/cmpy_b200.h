@@ -212,13 +212,6 @@ int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_dn, i
 int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                                int64_t ld_t, int world, const int64_t* h_col_bounds,
                                void* const* h_peer_ptrs, int max_ctas, void* stream);
-/* cmpy_transpose_pull_acc restricted to part `part` of `nparts` of every owner's column range
- * ([cb[q] + n_q*part/nparts, cb[q] + n_q*(part+1)/nparts), integer division), with at most max_ctas
- * CTAs (0 = default): the pull of one chunk of the up pass can overlap the next chunk. */
-int cmpy_transpose_pull_acc_part(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
-                                 int64_t ld_t, int world, const int64_t* h_col_bounds,
-                                 void* const* h_peer_ptrs, int part, int nparts, int max_ctas,
-                                 void* stream);
 int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                             int64_t ld_t, int world, const int64_t* h_col_bounds,
                             void* const* h_peer_ptrs, void* stream);

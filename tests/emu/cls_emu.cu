@@ -366,44 +366,4 @@ extern "C" int emu_weighted_elements(const long long* states, long long count, i
 
 // ---------------------------------------------------------------------------------
 // Partial pull transpose (peer.cuh, opt-in chunked second half of the sharded H.v): the tile loops of
-// peer_pull_part_kernel restated over host arrays, with the kernel's own column mapping
-// (peer_part_fill / peer_part_column).  peers[q] = YT slab of "rank" q.
-extern "C" int emu_pull_part(double* y, long long nrows, long long nd, long long row0, long long ld_t,
-                             int world, const long long* col_bounds, double* const* peers, int part, int nparts) {
-  if (world < 1 || world > PEER_MAX || nparts < 1 || part < 0 || part >= nparts) return 2;
-  PeerTable pt;
-  pt.world = world;
-  for (int q = 0; q < world; ++q) { pt.base[q] = peers[q]; pt.cb[q] = col_bounds[q]; }
-  pt.cb[world] = col_bounds[world];
-  PeerPart pp;
-  peer_part_fill(pp, pt, part, nparts);
-  const i64 vtot = pp.vstart[world];
-  const int TR = 32;
-  const i64 tiles_c = (vtot + 31) / 32, tiles_r = (nrows + TR - 1) / TR;
-  for (i64 t = 0; t < tiles_c * tiles_r; ++t) {
-    const i64 tr = t / tiles_c, tc = t - tr * tiles_c;
-    const i64 r0 = tr * TR, v0 = tc * 32;
-    double tile[32][TR + 1];
-    for (int k = 0; k < 32; ++k) {
-      const i64 v = v0 + k;
-      if (v < vtot) {
-        int q;
-        const i64 c = peer_part_column(pt, pp, v, q);
-        const double* src = pt.base[q] + (c - pt.cb[q]) * ld_t + row0 + r0;
-        for (int j = 0; j < TR; ++j) if (r0 + j < nrows) tile[k][j] = src[j];
-      }
-    }
-    for (int tx = 0; tx < 32; ++tx) {
-      const i64 v = v0 + tx;
-      if (v < vtot) {
-        int q;
-        const i64 c = peer_part_column(pt, pp, v, q);
-        for (int k = 0; k < TR; ++k) {
-          const i64 r = r0 + k;
-          if (r < nrows) y[r * nd + c] += tile[tx][k];
-        }
-      }
-    }
-  }
-  return 0;
-}
+

@@ -504,27 +504,3 @@ def test_random_lattices_long_rows(emu, case):
         assert rc == 0, (rc, case, eng)
         if cov.any():
             assert np.abs(y[cov] - ref[cov]).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (case, eng)
-
-
-@pytest.mark.parametrize("nparts", [1, 2, 3, 5])
-def test_partial_pull_column_mapping(emu, nparts):
-    """Opt-in chunked second half of the sharded H.v: the parts of every owner's column range tile the
-    columns exactly once (same data and expectation as tests/test_zz_experimental.py on the GPU)."""
-    world, nd, nu_total, row0, nrows = 3, 131, 70, 5, 50
-    cb = np.asarray([0, 40, 90, 131], dtype=np.int64)
-    rng = np.random.default_rng(4)
-    yts = [rng.standard_normal((cb[q + 1] - cb[q]) * nu_total) for q in range(world)]
-    y0 = rng.standard_normal(nrows * nd)
-    ref = y0.copy().reshape(nrows, nd)
-    for q in range(world):
-        ref[:, cb[q]:cb[q + 1]] += yts[q].reshape(cb[q + 1] - cb[q], nu_total)[:, row0:row0 + nrows].T
-    dp, llp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)
-    peers = (dp * world)(*[a.ctypes.data_as(dp) for a in yts])
-    emu.emu_pull_part.restype = ctypes.c_int
-    emu.emu_pull_part.argtypes = [dp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
-                                  ctypes.c_int, llp, ctypes.POINTER(dp), ctypes.c_int, ctypes.c_int]
-    y = y0.copy()
-    for part in range(nparts):
-        assert emu.emu_pull_part(y.ctypes.data_as(dp), nrows, nd, row0, nu_total, world, cb.ctypes.data_as(llp),
-                                 peers, part, nparts) == 0
-    np.testing.assert_array_equal(y.reshape(nrows, nd), ref)

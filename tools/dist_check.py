@@ -12,6 +12,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 cases = [(12, orc.chain_neighbors(12), 6, 6), (12, orc.square_neighbors(4, 3), 5, 7),
          (14, orc.chain_neighbors(14, True), 7, 7), (16, orc.square_neighbors(4, 4), 8, 8)]
+if len(sys.argv) > 1 and sys.argv[1] == "c4":   # only the benchmarked sector (plus one small case)
+    cases = [cases[0], cases[3]]
 for L, nb, nu, nd in cases:
     model = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0)
     full = model.hamilton_operator(nu, nd)
