@@ -180,10 +180,6 @@ API int cmpy_hubbard_create(int num_sites, const int64_t* h_up_states, int64_t n
   if (!rc && fixed_popcount)
     rc = op->configure_long(__builtin_popcountll((unsigned long long)h_dn_states[0]), bl.s1, bl.s2, h_eps);
   if (rc) { delete op; return rc; }
-  {  // engine of the default class-major launches (0 until engine 2 is measured on the target box)
-    const char* e = getenv("CMPY_CLS_ENGINE");
-    if (e && atoi(e) == 2) op->cls_engine = 2;
-  }
   *out = op;
   return CMPY_OK;
 }

@@ -164,8 +164,6 @@ struct HeisenbergOp : cmpy_op_s {
   int threads = 256, blocks_per_sm = 1;
   // fast path for more than 16 sites: sub-row launches of the class-major kernel (hubbard_cls.cuh)
   LongTables lng;
-  LongTables lng2;      // engine 2 of the class-major kernel
-  int fast_engine = 0;  // engine the default fast path uses (CMPY_CLS_ENGINE)
   std::vector<int> slow_pt;   // popcounts of the high part left to heis_row_kernel
   SpinDiag sd;
   double w_hop = 0.0;
@@ -176,7 +174,7 @@ struct HeisenbergOp : cmpy_op_s {
   ~HeisenbergOp() override {
     cudaFree(d_off); cudaFree(d_lo_list); cudaFree(d_cls_off); cudaFree(d_lo_rank); cudaFree(d_bonds);
     cudaFree(d_zero_u32); cudaFree(d_zero_f64);
-    lng.release(); lng2.release();
+    lng.release();
   }
 
   HeisParams params() const {
@@ -321,25 +319,10 @@ struct HeisenbergOp : cmpy_op_s {
     if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, true, true>, smem_optin);
     if (rc) return rc;
     fast_ok = true;
-    {  // engine 2 of the class-major kernel (chunked tasks): same sub-rows, its own table set
-      std::vector<int> slow2;
-      rc = build_long_tables(lng2, num_sites, n_up, size, (int)bi.size(), bi.data(), bj.data(), 0, eps0,
-                             smem_optin, &slow2, 2);
-      if (rc) return rc;
-      if (lng2.ok && slow2 != slow_pt) lng2.release();
-      if (lng2.ok) {
-        rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, true, true, 2>, smem_optin);
-        if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, true, true, 2>, smem_optin);
-        if (rc) return rc;
-      }
-      const char* e = getenv("CMPY_CLS_ENGINE");
-      fast_engine = (e && atoi(e) == 2 && lng2.ok) ? 2 : 0;
-    }
     return CMPY_OK;
   }
 
-  int apply_fast(const double* x, double* y, const LzCtx& lz, cudaStream_t st, int eng) {
-    LongTables& lng = eng == 2 ? this->lng2 : this->lng;
+  int apply_fast(const double* x, double* y, const LzCtx& lz, cudaStream_t st) {
     HubParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.num_up = 1; hp.num_dn = size; hp.up_states = d_zero_u32; hp.e_up = d_zero_f64;
@@ -360,11 +343,9 @@ struct HeisenbergOp : cmpy_op_s {
       if (lz.enabled) {
         cp.hp.lz = lz; cp.hp.lz.partials = d_partials; cp.hp.lz.ticket = d_ticket;
         cp.hp.lz.enabled = launches == 0 ? 1 : 2;
-        if (eng == 2) hub_cls_kernel<true, 1024, 8, true, true, 2><<<(int)g, 1024, S.cls.smem, st>>>(cp);
-        else hub_cls_kernel<true, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+        hub_cls_kernel<true, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
       } else {
-        if (eng == 2) hub_cls_kernel<false, 1024, 8, true, true, 2><<<(int)g, 1024, S.cls.smem, st>>>(cp);
-        else hub_cls_kernel<false, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+        hub_cls_kernel<false, 1024, 8, true, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
       }
       KERNEL_CHECK();
       ++launches;
@@ -393,10 +374,7 @@ struct HeisenbergOp : cmpy_op_s {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     if (variant == 5 && !(fast_ok && aligned16))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant not available for this spin sector");
-    if (variant == 9 && !(fast_ok && lng2.ok && aligned16))
-      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant (engine 2) not available for this spin sector");
-    if (variant == 9) return apply_fast(x, y, lz, st, 2);
-    if (fast_ok && aligned16 && variant != 1) return apply_fast(x, y, lz, st, variant == 5 ? 0 : fast_engine);
+    if (fast_ok && aligned16 && variant != 1) return apply_fast(x, y, lz, st);
     HeisParams p = params();
     p.x = x; p.y = y;
     size_t smem = sizeof(double) * (size_t)max_len;

@@ -32,9 +32,6 @@
 #include "hubbard_seg.cuh"
 
 #define CLS_MAX_CLS 12
-#define CLS2_MAX_PIECES 128   // engine 2: upper bound on the work pieces per phase
-#define CLS2_DEF_PIECES 32    // default: one piece per warp of a 1024-thread CTA (measured: 32: 2.16 ms,
-                              // 64: 2.27 ms, 128: 2.46 ms on the 4x4 sector, dn-only pass)
 #define CLS_ZREG 96  // zero region appended to xs (target of HH list padding)
 
 struct ClsLayout {
@@ -59,24 +56,9 @@ struct ClsLayout {
   int off_lh_hi;     // u16 [nlh][nhi]     sbase of segment dh^bit | par << 14 | bit << 15
   int off_lh_lo;     // u8  [nlh][2][nq]   per value of the dh bit: r' | par << 7, or the slack slot
   int off_seg_delta; // i16 [nseg + 1]     (sbase - goff) of the segments in natural order
-  // ---- engine 2 (chunked tasks, hoisted per-lane state; see cls2_phase_a / cls2_phase_b) ----
-  int eng;           // 0: one (k, r) / dh item per warp pass; 2: chunked tasks
-  int zbase;         // first slot of the zero region (= xs_elems)
-  int nta, ntb;      // phase-A / phase-B task counts
-  int off_task_a;    // u32 [nta]  k | r0 << 8 | nr << 16   (nr consecutive ranks r of class k)
-  int off_task_b;    // u32 [ntb]  k | jj0 << 8 | njj << 16 (njj consecutive segments of class k)
-  int off_hhp_cm;    // u32 [nseg] HH list pointer of the segments in class-major order
-  int off_lhj;       // u32 [nlh][nseg] per class-major segment: slot of the source segment when the
-                     //     dl bit is clear (bits 0-13) / set (bits 14-27), the zero region when the
-                     //     hop is not allowed for that value; bit 31 = parity of the dh part
-  int off_lhq;       // u16 [nlh][nq]   per (k, r): r' | parity of the dl part << 7 | dl bit << 8 |
-                     //     source class exists << 9
-  int npieces;       // work pieces per phase
-  uint16_t ptr_a[CLS2_MAX_PIECES + 1], ptr_b[CLS2_MAX_PIECES + 1];  // tasks of piece i: [ptr[i], ptr[i+1])
   int bytes;
 };
 
-#define CLS2_MAX_LH 4   // LH bonds whose per-lane entries engine 2 keeps in registers
 
 // Long rows (more than 16 sites): the dn string is (dtop, drest), drest = low 16 bits.  For a
 // fixed dtop the strings are contiguous in the row (a "sub-row" of C(16, n_dn - popc(dtop))
@@ -151,37 +133,6 @@ CLS_HD double cls_flip(double v, uint32_t signmask) {
 #endif
 }
 CLS_HD int cls_min(int a, int b) { return a < b ? a : b; }
-// Engine 2 addresses shared memory through explicit byte addresses (32-bit shared-space addresses
-// on the device, so that "per-lane base + warp-uniform offset" is one LEA/IADD per access instead
-// of a re-derivation from the buffer base; plain pointers on the host).
-#ifdef CMPY_EMU
-static std::vector<uintptr_t>* g_cls_trace = nullptr;   // tests/emu only: addresses of one lane's loads, in order
-#endif
-#ifdef __CUDA_ARCH__
-typedef uint32_t cls_addr;
-__device__ __forceinline__ cls_addr cls_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ double cls_ld(cls_addr a) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ double cls_ld_y(cls_addr a) { return cls_ld(a); }
-__device__ __forceinline__ void cls_st(cls_addr a, double v) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
-#else
-typedef uintptr_t cls_addr;
-inline cls_addr cls_base(const void* p) { return (uintptr_t)p; }
-inline double cls_ld(cls_addr a) {
-#ifdef CMPY_EMU
-  if (g_cls_trace) g_cls_trace->push_back(a);
-#endif
-  return *reinterpret_cast<const double*>(a);
-}
-inline double cls_ld_y(cls_addr a) { return *reinterpret_cast<const double*>(a); }   // predicated load: not traced
-inline void cls_st(cls_addr a, double v) { *reinterpret_cast<double*>(a) = v; }
-#endif
-
 // ---- phase A body: one (k, r) pair, T blocks of 32 dh-segments (lanes along jj) ----
 template <int T, bool SPIN>
 CLS_HD void cls_phase_a(const ClsLayout& L, const SpinDiag& sd,
@@ -288,210 +239,13 @@ CLS_HD void cls_phase_b(const ClsLayout& L, const double* __restrict__ xs,
     if (lane + 32 * t < sk) yp0[32 * t] += hop0 * (hp[t] - hn[t]);
 }
 
-// ---------------------------------------------------------------------------------
-// Engine 2: the same class-major layout and hop lists, walked in chunked tasks so that
-// everything that depends on the lane only is computed once per task instead of once per
-// (k, r) / dh item:
-//   phase A  task = nr consecutive ranks r of one class k, lanes along jj.  Hoisted per lane:
-//            slot offsets, popcount of the dh part (diagonal), and the LH source segments
-//            (lhj).  LL hops as in engine 0.  The LH hops move here from phase B: for a fixed
-//            (k, r) the source rank r', the dl bit and the dl parity are warp-uniform (lhq),
-//            the source segment is the hoisted per-lane entry -> x[src + r'] is an odd-pitch
-//            (conflict-free) access and bonds whose source class does not exist are skipped
-//            for the whole warp.
-//   phase B  task = njj consecutive segments of one class, lanes along r: HH hops only.
-// Measured on B200 (4x4 sector, dn-only pass, profiles/r1_prof_cls_eng2_dn_c4.summary.txt,
-// profiles/r1_engine2_bench.jsonl).  First version (padded pair lists as in engine 0): 5 % fewer
-// issued instructions and 15 % fewer shared-memory wavefronts than engine 0 and the same time
-// (2.16 vs 2.12 ms); 512 / 768-thread CTAs, which let ptxas keep several loads of a hop list in
-// flight, are slower (2.45 / 2.26 ms).  2/3 of the instructions of both engines sit in the three
-// hop loops (LL 21 %, HH 19 %, LH 26 %), and the pass is bound by the latency of its dependent
-// shared-memory loads x 8 warps per scheduler rather than by issue slots (60 %) or the
-// shared-memory pipe (72-78 %).  With unpadded single-entry lists (2.12 ms) and the list entries /
-// pointers loaded one step ahead (2.05 ms; 16-site chain 1.54 vs 1.60 ms; 20-site slab 0.692 vs
-// 0.704 ms) it is 3-4 % ahead of engine 0.  Engine 0 stays the default this round; engine 2 is
-// opt-in (variants 9 / 10, CMPY_CLS_ENGINE=2).  The phase bodies of both engines run lane by lane
-// on the CPU in tests/test_cls_emulation.py.
-// ---------------------------------------------------------------------------------
-template <int T, bool SPIN>
-CLS_HD void cls2_phase_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* __restrict__ tab,
-                         const double* __restrict__ xs, double* __restrict__ ys, uint32_t task,
-                         uint32_t ups, double eu, double u0, double hop0, int lane) {
-  const int k = (int)(task & 0xffu), r0 = (int)((task >> 8) & 0xffu), nr = (int)(task >> 16);
-  const int hk = L.H[k], pk = L.P[k], xb = L.xbase[k], nlh = L.nlh;
-  const uint8_t* __restrict__ ll_ent = tab + L.off_ll_ent;
-  const uint32_t* __restrict__ ll_ptr = reinterpret_cast<const uint32_t*>(tab + L.off_ll_ptr) + L.qoff[k];
-  const uint16_t* __restrict__ dl_of_q = reinterpret_cast<const uint16_t*>(tab + L.off_dl_of_q) + L.qoff[k];
-  const uint16_t* __restrict__ dh_list = reinterpret_cast<const uint16_t*>(tab + L.off_dh_list) + L.hoff[k];
-  const uint32_t* __restrict__ lhj = reinterpret_cast<const uint32_t*>(tab + L.off_lhj) + L.hoff[k];
-  const uint16_t* __restrict__ lhq = reinterpret_cast<const uint16_t*>(tab + L.off_lhq) + L.qoff[k];
-  const cls_addr xs_a = cls_base(xs);
-  const cls_addr y_minus_x = cls_base(ys) - xs_a;   // the two buffers have the same layout
-  // hoisted per-lane state; lanes past the class recompute its last segment and never store
-  cls_addr xa[T];       // address of xs[(jj, r = 0)]
-  uint32_t dhs[T];      // dh bits of the lane's segments, already shifted to their place in the string
-  uint32_t lh[CLS2_MAX_LH][T];
-  double dgh[T];        // eu + u0 * popc(ups & dh part)
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int jj = cls_min(lane + 32 * t, hk - 1);
-    xa[t] = xs_a + (cls_addr)(xb + jj * pk) * 8u;
-    dhs[t] = (uint32_t)dh_list[jj] << L.m;
-    dgh[t] = SPIN ? 0.0 : eu + u0 * (double)cls_popc(ups & dhs[t]);
-#pragma unroll
-    for (int b = 0; b < CLS2_MAX_LH; ++b) lh[b][t] = b < nlh ? lhj[b * L.nseg + jj] : 0u;
-  }
-  uint32_t pp_next = ll_ptr[r0];
-#pragma unroll 1
-  for (int r = r0; r < r0 + nr; ++r) {
-    double ap[T], an[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) { ap[t] = 0.0; an[t] = 0.0; }
-    {  // LL hops: one list per (k, r), '+' entries then '-' entries (no padding).  The entry of
-       // the next iteration and the list pointer of the next column are loaded one step ahead so
-       // that the dependent chain per hop is one shared-memory load, not two (the over-read by one
-       // element stays inside the table blob).
-      const uint32_t pp = pp_next;
-      pp_next = ll_ptr[r + 1];
-      const uint8_t* __restrict__ ent = ll_ent + (pp & 0xffffu);
-      const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
-      uint32_t e_next = ent[0];
-      int i = 0;
-#pragma unroll 1
-      for (; i < npos; ++i) {
-        const cls_addr e0 = (cls_addr)e_next * 8u;
-        e_next = ent[i + 1];
-        double v0[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
-#pragma unroll
-        for (int t = 0; t < T; ++t) ap[t] += v0[t];
-      }
-#pragma unroll 1
-      for (; i < ntot; ++i) {
-        const cls_addr e0 = (cls_addr)e_next * 8u;
-        e_next = ent[i + 1];
-        double v0[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) v0[t] = cls_ld(xa[t] + e0);
-#pragma unroll
-        for (int t = 0; t < T; ++t) an[t] += v0[t];
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < CLS2_MAX_LH; ++b) {  // LH hops
-      if (b < nlh) {
-        const uint32_t w = lhq[b * L.nq + r];
-        if (w & 0x200u) {
-          const cls_addr xq = xs_a + (cls_addr)(w & 0x7fu) * 8u;
-          const int sh = (w & 0x100u) ? 14 : 0;
-          const uint32_t sgn = (w & 0x80u) << 24;   // parity of the dl part -> sign bit position
-          double v[T];
-#pragma unroll
-          for (int t = 0; t < T; ++t) v[t] = cls_ld(xq + (cls_addr)((lh[b][t] >> sh) & 0x3fffu) * 8u);
-#pragma unroll
-          for (int t = 0; t < T; ++t) ap[t] += cls_flip(v[t], (lh[b][t] ^ sgn) & 0x80000000u);
-        }
-      }
-    }
-    const uint32_t dlbits = dl_of_q[r];
-    const double dgl = SPIN ? 0.0 : u0 * (double)cls_popc(ups & dlbits);
-    const cls_addr r8 = (cls_addr)r * 8u;
-    double xv[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) xv[t] = cls_ld(xa[t] + r8);   // (clamped lanes re-read the last segment)
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (lane + 32 * t < hk) {
-        double diag;
-        if (SPIN) {  // ups carries the top bits of the spin string (dtop << 16)
-          const uint32_t sfull = ups | dhs[t] | dlbits;
-          int cnt = 0;
-          for (int i = 0; i < sd.ndelta; ++i) cnt += cls_popc((sfull ^ (sfull >> sd.delta[i])) & sd.dmask[i]);
-          diag = sd.e0 + sd.escale * (double)cnt;
-        } else {
-          diag = dgh[t] + dgl;   // = eu + u0 * popc(ups & dn) up to one rounding
-        }
-        cls_st(xa[t] + r8 + y_minus_x, diag * xv[t] + hop0 * (ap[t] - an[t]));
-      }
-    }
-  }
-}
-
-template <int T>
-CLS_HD void cls2_phase_b(const ClsLayout& L, const unsigned char* __restrict__ tab,
-                         const double* __restrict__ xs, double* __restrict__ ys, uint32_t task,
-                         double hop0, int lane) {
-  const int k = (int)(task & 0xffu), jj0 = (int)((task >> 8) & 0xffu), njj = (int)(task >> 16);
-  const int sk = L.S[k], pk = L.P[k];
-  const uint32_t* __restrict__ hhp = reinterpret_cast<const uint32_t*>(tab + L.off_hhp_cm) + L.hoff[k];
-  const uint16_t* __restrict__ hh_ent = reinterpret_cast<const uint16_t*>(tab + L.off_hh_ent);
-  const cls_addr xl = cls_base(xs) + (cls_addr)lane * 8u;
-  const cls_addr yl = cls_base(ys) + (cls_addr)(L.xbase[k] + lane) * 8u;
-  uint32_t pp_next = hhp[jj0];
-#pragma unroll 1
-  for (int jj = jj0; jj < jj0 + njj; ++jj) {
-    const uint32_t pp = pp_next;
-    pp_next = hhp[jj + 1];
-    const int npos = (int)((pp >> 16) & 0xffu), ntot = (int)(pp >> 24);
-    if (ntot == 0) continue;
-    double hp[T], hn[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) { hp[t] = 0.0; hn[t] = 0.0; }
-    const uint16_t* __restrict__ ent = hh_ent + (pp & 0xffffu);
-    uint32_t e_next = ent[0];
-    int i = 0;
-#pragma unroll 1
-    for (; i < npos; ++i) {
-      const cls_addr q0 = xl + (cls_addr)e_next * 8u;
-      e_next = ent[i + 1];
-      double v0[T];
-#pragma unroll
-      for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
-#pragma unroll
-      for (int t = 0; t < T; ++t) hp[t] += v0[t];
-    }
-#pragma unroll 1
-    for (; i < ntot; ++i) {
-      const cls_addr q0 = xl + (cls_addr)e_next * 8u;
-      e_next = ent[i + 1];
-      double v0[T];
-#pragma unroll
-      for (int t = 0; t < T; ++t) v0[t] = cls_ld(q0 + 256u * t);
-#pragma unroll
-      for (int t = 0; t < T; ++t) hn[t] += v0[t];
-    }
-    const cls_addr yp = yl + (cls_addr)(jj * pk) * 8u;
-#pragma unroll
-    for (int t = 0; t < T; ++t)
-      if (lane + 32 * t < sk) cls_st(yp + 256u * t, cls_ld_y(yp + 256u * t) + hop0 * (hp[t] - hn[t]));
-  }
-}
-
-// warp-level dispatch on the number of 32-lane blocks (classes are at most 96 long / high)
-template <bool SPIN>
-CLS_HD void cls2_task_a(const ClsLayout& L, const SpinDiag& sd, const unsigned char* tab, const double* xs,
-                        double* ys, uint32_t task, uint32_t ups, double eu, double u0, double hop0, int lane) {
-  const int hk = L.H[task & 0xffu];
-  if (hk <= 32) cls2_phase_a<1, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
-  else if (hk <= 64) cls2_phase_a<2, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
-  else cls2_phase_a<3, SPIN>(L, sd, tab, xs, ys, task, ups, eu, u0, hop0, lane);
-}
-CLS_HD void cls2_task_b(const ClsLayout& L, const unsigned char* tab, const double* xs, double* ys,
-                        uint32_t task, double hop0, int lane) {
-  const int sk = L.S[task & 0xffu];
-  if (sk <= 32) cls2_phase_b<1>(L, tab, xs, ys, task, hop0, lane);
-  else if (sk <= 64) cls2_phase_b<2>(L, tab, xs, ys, task, hop0, lane);
-  else cls2_phase_b<3>(L, tab, xs, ys, task, hop0, lane);
-}
-
 __device__ __forceinline__ int seg_delta_g(const ClsParams& cp, int si) {
   return (int)reinterpret_cast<const int16_t*>(cp.blob + cp.lay.off_seg_delta)[si];
 }
 
 // smem: [table blob][xs: xs_elems + CLS_ZREG doubles][ys: xs_elems doubles]
 // UPG = 0 compiles the up-hop gathers out (row-slab launches of the sharded operator).
-template <bool LZ, int NT, int UPG_, bool LONG = false, bool SPIN = false, int ENG = 0>
+template <bool LZ, int NT, int UPG_, bool LONG = false, bool SPIN = false>
 __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
   constexpr bool WITH_UP = UPG_ > 0;
   constexpr int UPG = WITH_UP ? UPG_ : 1;
@@ -619,12 +373,6 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + b));
     }
     // ---- phase A: lanes along jj, LL hops + diagonal -> ys ----
-    if (ENG == 2) {
-      const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
-      for (int pc = warp; pc < L.npieces; pc += NW)
-        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it)
-          cls2_task_a<SPIN>(L, cp.sd, tab, xs, ys, task_a[it], ups, eu, u0, hop0, lane);
-    } else
     for (int it = warp; it < L.na; it += NW) {
       const int q = item_a[it];
       const int k = k_of_q[q];
@@ -639,11 +387,6 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
     __syncthreads();
     CLS_TICK(2)
     // ---- phase B: lanes along r, HH + LH hops accumulated into ys ----
-    if (ENG == 2) {
-      const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
-      for (int pc = warp; pc < L.npieces; pc += NW)
-        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it) cls2_task_b(L, tab, xs, ys, task_b[it], hop0, lane);
-    } else
     for (int it = warp; it < L.nb; it += NW) {
       const int dh = item_b[it];
       const int k = hi_k[dh];
@@ -761,8 +504,7 @@ struct ClsTables {
 // Builds the class-major tables for the dn species.  ok=false (no error) when the sector is
 // outside what the kernel supports (non-sector string list, odd row length, row too long for
 // shared memory, classes longer than 96).
-// Host-only part (no CUDA calls): layout, table blob and the column-pair maps.  eng selects the
-// table set: 0 = per-item phases (cls_phase_a / cls_phase_b), 2 = chunked tasks (cls2_*).
+// Host-only part (no CUDA calls): layout, table blob and the column-pair maps.
 struct ClsHost {
   ClsLayout lay;
   std::vector<unsigned char> blob;
@@ -774,7 +516,7 @@ struct ClsHost {
 
 static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                           const int* s1, const int* s2, int sign_width, const double* eps,
-                          i64 smem_optin, int eng = 0) {
+                          i64 smem_optin) {
   T.ok = false;
   const u64* B = host_binom();
   if (n_dn < 0 || n_dn > num_sites || num_sites < 2) return CMPY_OK;
@@ -867,15 +609,6 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
   // pack a ('+' list, '-' list) into pairs, each part padded to an even length with `dummy`
   auto pack = [&](const std::vector<uint16_t>& pos, const std::vector<uint16_t>& neg, uint16_t dummy,
                   auto& out, uint32_t& ptr) -> bool {
-    if (eng == 2) {  // engine 2: plain lists, no padding; the pointer counts entries, not pairs
-      const size_t start = out.size();
-      if (start >= 65536 || pos.size() + neg.size() > 255) return false;
-      typedef typename std::remove_reference<decltype(out)>::type::value_type E;
-      for (uint16_t v : pos) out.push_back((E)v);
-      for (uint16_t v : neg) out.push_back((E)v);
-      ptr = (uint32_t)start | ((uint32_t)pos.size() << 16) | ((uint32_t)(pos.size() + neg.size()) << 24);
-      return true;
-    }
     if (out.size() & 1) out.push_back(dummy);
     const size_t start = out.size();
     const size_t np2 = (pos.size() + 1) / 2, nn2 = (neg.size() + 1) / 2;
@@ -954,138 +687,26 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
     if (hi_k[dh] != 0xff) item_b.push_back((uint16_t)dh);
   L.na = (int)item_a.size();
   L.nb = (int)item_b.size();
-  L.eng = eng;
-  L.zbase = zbase;
-  // ---- engine 2: chunked tasks, class-major HH pointers, LH tables split into a per-lane part
-  //      (lhj, indexed by the class-major segment) and a warp-uniform part (lhq, indexed by (k, r)) ----
-  std::vector<uint32_t> task_a, task_b, hhp_cm, lhj;
-  std::vector<uint16_t> lhq;
-  if (eng == 2) {
-    if (L.nlh > CLS2_MAX_LH || m > 8 || hb > 8) return CMPY_OK;  // task fields are 8 bits wide
-    // The (k, r) columns of phase A / (k, jj) segments of phase B, in class-major order, are cut
-    // into npieces contiguous pieces of about equal estimated cost; a piece that spans a class
-    // boundary becomes several tasks.  Warp w of the CTA takes the pieces w, w + NW, ...
-    // The cost model counts issued instructions of the compiled loops (SASS of sm_100a):
-    //   phase A, per column: 25 + entries * (5 + 3 T) + LH bonds * (9 + 8 T) + 10 T   (T = 32-lane blocks)
-    //   phase B, per segment: 12 + entries * (5 + 2 T) + 6 T
-    int npieces = CLS2_DEF_PIECES;
-    if (const char* e = getenv("CMPY_CLS_PIECES")) npieces = atoi(e);
-    if (npieces < 1) npieces = 1;
-    if (npieces > CLS2_MAX_PIECES) npieces = CLS2_MAX_PIECES;
-    L.npieces = npieces;
-    auto partition = [&](std::vector<uint32_t>& out, uint16_t* ptr, const int* loop_dim, auto&& cost) {
-      double total = 0.0;
-      for (int k = 0; k <= m; ++k)
-        if (L.H[k] > 0)
-          for (int c = 0; c < loop_dim[k]; ++c) total += cost(k, c);
-      out.clear();
-      for (int i = 0; i <= CLS2_MAX_PIECES; ++i) ptr[i] = 0;
-      double acc = 0.0;
-      int piece = 0, cur_k = -1, c0 = 0, n = 0;
-      auto flush = [&]() {
-        if (n > 0) out.push_back((uint32_t)cur_k | ((uint32_t)c0 << 8) | ((uint32_t)n << 16));
-        n = 0;
-      };
-      for (int k = 0; k <= m; ++k) {
-        if (L.H[k] <= 0) continue;
-        for (int c = 0; c < loop_dim[k]; ++c) {
-          const double w = cost(k, c);
-          // close the piece when its share of the total is used up (never leave a piece empty
-          // while work remains, never open more than npieces pieces)
-          if (piece + 1 < npieces && acc + 0.5 * w > total * (piece + 1) / npieces &&
-              (n > 0 || (int)out.size() > ptr[piece])) {
-            flush();
-            ptr[++piece] = (uint16_t)out.size();
-          }
-          if (n > 0 && cur_k != k) flush();
-          if (n == 0) { cur_k = k; c0 = c; }
-          ++n;
-          acc += w;
-        }
-      }
-      flush();
-      while (piece < CLS2_MAX_PIECES) ptr[++piece] = (uint16_t)out.size();
-    };
-    auto cost_a = [&](int k, int r) {
-      const int T = (L.H[k] + 31) / 32;
-      const uint32_t pp = ll_ptr[L.qoff[k] + r];
-      return 25.0 + (double)(pp >> 24) * (5.0 + 3.0 * T) + (double)L.nlh * (9.0 + 8.0 * T) + 10.0 * T;
-    };
-    auto cost_b = [&](int k, int jj) {
-      const int T = (L.S[k] + 31) / 32;
-      const uint32_t pp = hh_ptr[dh_list[L.hoff[k] + jj]];
-      return 12.0 + (double)(pp >> 24) * (5.0 + 2.0 * T) + 6.0 * T;
-    };
-    partition(task_a, L.ptr_a, L.S, cost_a);   // lanes along jj (H_k), loop over r (S_k)
-    partition(task_b, L.ptr_b, L.H, cost_b);   // lanes along r (S_k), loop over jj (H_k)
-    L.nta = (int)task_a.size();
-    L.ntb = (int)task_b.size();
-    hhp_cm.assign(std::max(nseg, 1), 0);
-    for (int sgi = 0; sgi < nseg; ++sgi) hhp_cm[sgi] = hh_ptr[dh_list[sgi]];
-    lhj.assign((size_t)std::max(1, L.nlh) * std::max(nseg, 1), 0);
-    lhq.assign((size_t)std::max(1, L.nlh) * nlo, 0);
-    for (int qb = 0; qb < L.nlh; ++qb) {
-      const int b = lh[qb];
-      const int a = s1[b], c = s2[b] - m;  // a inside dl, c inside dh
-      for (int sgi = 0; sgi < nseg; ++sgi) {
-        const int dh = dh_list[sgi];
-        const int nh = dh ^ (1 << c);
-        const int bit = (dh >> c) & 1;
-        const uint32_t par = (uint32_t)parity((u64)dh << m, m - 1, s2[b]);  // bits of dh strictly below c
-        const uint32_t src = (hi_k[nh] != 0xff) ? (uint32_t)hi_sbase[nh] : (uint32_t)zbase;
-        // dl bit clear: the particle sits on c in dh (bit = 1) and the source has it on a
-        const uint32_t off_clear = bit ? src : (uint32_t)zbase;
-        const uint32_t off_set = bit ? (uint32_t)zbase : src;
-        lhj[(size_t)qb * nseg + sgi] = off_clear | (off_set << 14) | (par << 31);
-      }
-      for (int q = 0; q < nlo; ++q) {
-        const int dl = dl_of_q[q], k = k_of_q[q];
-        const int bit_lo = (dl >> a) & 1;
-        const int kp = k + (bit_lo ? -1 : 1);  // class of the source segment
-        uint16_t e = 0;
-        if (kp >= 0 && kp <= m && L.H[kp] > 0 && L.H[k] > 0) {
-          const int nl = dl ^ (1 << a);
-          const int par = parity((u64)dl, a, m);  // bits of dl strictly above a
-          e = (uint16_t)(lo_rank[nl] | (par << 7) | (bit_lo << 8) | (1 << 9));
-        }
-        lhq[(size_t)qb * nlo + q] = e;
-      }
-    }
-  }
   // energies: eps uniform -> eps * n_dn summed like weighted_element (ascending adds)
   { double v = 0; for (int i = 0; i < n_dn; ++i) v += eps[0]; T.e_dn_const = v; }
   // blob layout
   int o = 0;
   auto place = [&](int& off, size_t bytes) { off = o; o = align16(o + (int)std::max<size_t>(bytes, 16)); };
-  if (eng == 2) {
-    place(L.off_task_a, 4 * task_a.size());
-    place(L.off_task_b, 4 * task_b.size());
-    place(L.off_dl_of_q, 2 * nlo);
-    place(L.off_ll_ptr, 4 * nlo);
-    place(L.off_ll_ent, ll_ent.size());
-    place(L.off_dh_list, 2 * dh_list.size());
-    place(L.off_hhp_cm, 4 * hhp_cm.size());
-    place(L.off_hh_ent, 2 * hh_ent.size());
-    place(L.off_lhj, 4 * lhj.size());
-    place(L.off_lhq, 2 * lhq.size());
-    place(L.off_seg_delta, 2 * seg_delta.size());
-  } else {
-    place(L.off_item_a, 2 * item_a.size());
-    place(L.off_item_b, 2 * item_b.size());
-    place(L.off_k_of_q, nlo);
-    place(L.off_dl_of_q, 2 * nlo);
-    place(L.off_ll_ptr, 4 * nlo);
-    place(L.off_ll_ent, ll_ent.size());
-    place(L.off_dh_list, 2 * dh_list.size());
-    place(L.off_hi_goff, 2 * nhi);
-    place(L.off_hi_sbase, 2 * nhi);
-    place(L.off_hi_k, nhi);
-    place(L.off_hh_ptr, 4 * nhi);
-    place(L.off_hh_ent, 2 * hh_ent.size());
-    place(L.off_lh_hi, 2 * lh_hi.size());
-    place(L.off_lh_lo, lh_lo.size());
-    place(L.off_seg_delta, 2 * seg_delta.size());
-  }
+  place(L.off_item_a, 2 * item_a.size());
+  place(L.off_item_b, 2 * item_b.size());
+  place(L.off_k_of_q, nlo);
+  place(L.off_dl_of_q, 2 * nlo);
+  place(L.off_ll_ptr, 4 * nlo);
+  place(L.off_ll_ent, ll_ent.size());
+  place(L.off_dh_list, 2 * dh_list.size());
+  place(L.off_hi_goff, 2 * nhi);
+  place(L.off_hi_sbase, 2 * nhi);
+  place(L.off_hi_k, nhi);
+  place(L.off_hh_ptr, 4 * nhi);
+  place(L.off_hh_ent, 2 * hh_ent.size());
+  place(L.off_lh_hi, 2 * lh_hi.size());
+  place(L.off_lh_lo, lh_lo.size());
+  place(L.off_seg_delta, 2 * seg_delta.size());
   L.bytes = o;
   const int xs_total = (L.xs_elems + CLS_ZREG + 1) & ~1;
   T.smem = (size_t)L.bytes + sizeof(double) * ((size_t)xs_total + (size_t)L.xs_elems);
@@ -1101,23 +722,15 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
   { auto t = narrow16(dh_list); put(L.off_dh_list, t.data(), 2 * t.size()); }
   put(L.off_hh_ent, hh_ent.data(), 2 * hh_ent.size());
   { std::vector<int16_t> t(seg_delta.size()); for (size_t i = 0; i < t.size(); ++i) t[i] = (int16_t)seg_delta[i]; put(L.off_seg_delta, t.data(), 2 * t.size()); }
-  if (eng == 2) {
-    put(L.off_task_a, task_a.data(), 4 * task_a.size());
-    put(L.off_task_b, task_b.data(), 4 * task_b.size());
-    put(L.off_hhp_cm, hhp_cm.data(), 4 * hhp_cm.size());
-    put(L.off_lhj, lhj.data(), 4 * lhj.size());
-    put(L.off_lhq, lhq.data(), 2 * lhq.size());
-  } else {
-    put(L.off_item_a, item_a.data(), 2 * item_a.size());
-    put(L.off_item_b, item_b.data(), 2 * item_b.size());
-    { auto t = narrow8(k_of_q); put(L.off_k_of_q, t.data(), t.size()); }
-    { auto t = narrow16(hi_goff); put(L.off_hi_goff, t.data(), 2 * t.size()); }
-    { auto t = narrow16(hi_sbase); put(L.off_hi_sbase, t.data(), 2 * t.size()); }
-    { auto t = narrow8(hi_k); put(L.off_hi_k, t.data(), t.size()); }
-    put(L.off_hh_ptr, hh_ptr.data(), 4 * hh_ptr.size());
-    put(L.off_lh_hi, lh_hi.data(), 2 * lh_hi.size());
-    put(L.off_lh_lo, lh_lo.data(), lh_lo.size());
-  }
+  put(L.off_item_a, item_a.data(), 2 * item_a.size());
+  put(L.off_item_b, item_b.data(), 2 * item_b.size());
+  { auto t = narrow8(k_of_q); put(L.off_k_of_q, t.data(), t.size()); }
+  { auto t = narrow16(hi_goff); put(L.off_hi_goff, t.data(), 2 * t.size()); }
+  { auto t = narrow16(hi_sbase); put(L.off_hi_sbase, t.data(), 2 * t.size()); }
+  { auto t = narrow8(hi_k); put(L.off_hi_k, t.data(), t.size()); }
+  put(L.off_hh_ptr, hh_ptr.data(), 4 * hh_ptr.size());
+  put(L.off_lh_hi, lh_hi.data(), 2 * lh_hi.size());
+  put(L.off_lh_lo, lh_lo.data(), lh_lo.size());
   T.ok = true;
   return CMPY_OK;
 }
@@ -1126,10 +739,10 @@ static int build_cls_host(ClsHost& T, int num_sites, int n_dn, i64 num_dn, int n
 // the sector is outside what the kernel supports.
 static int build_cls_tables(ClsTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                             const int* s1, const int* s2, int sign_width, const double* eps,
-                            i64 smem_optin, int eng = 0) {
+                            i64 smem_optin) {
   T.ok = false;
   ClsHost H;
-  int rc = build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, smem_optin, eng);
+  int rc = build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, smem_optin);
   if (rc || !H.ok) return rc;
   T.lay = H.lay; T.e_dn_const = H.e_dn_const; T.smem = H.smem;
   CU_CHECK(cudaMalloc(&T.d_blob, H.blob.size()));
@@ -1199,7 +812,7 @@ struct LongHost {
 
 static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn, int nbonds,
                              const int* s1, const int* s2, int sign_width, const double* eps,
-                             i64 smem_optin, std::vector<int>* skipped = nullptr, int eng = 0,
+                             i64 smem_optin, std::vector<int>* skipped = nullptr,
                              LongHost* mirror = nullptr) {
   if (!mirror) T.release();
   const u64* B = host_binom();
@@ -1241,11 +854,11 @@ static int build_long_tables(LongTables& T, int num_sites, int n_dn, i64 num_dn,
     bool cls_ok;
     if (mirror) {
       rc = build_cls_host(HS.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
-                          eps, smem_optin, eng);
+                          eps, smem_optin);
       cls_ok = HS.cls.ok;
     } else {
       rc = build_cls_tables(S.cls, R, nr, S.row_len, (int)lo1.size(), lo1.data(), lo2.data(), sign_width,
-                            eps, smem_optin, eng);
+                            eps, smem_optin);
       cls_ok = S.cls.ok;
     }
     if (rc) { S.release(); return rc; }

@@ -58,10 +58,6 @@ struct HubbardOp : cmpy_op_s {
   bool seg_wide = false;     // 1024-thread CTAs (one CTA per SM, long rows)
   LongTables lng;            // rows of more than 16 sites: sub-row launches of the class-major kernel
   ClsTables cls;             // class-major two-phase kernel (uniform models, long rows)
-  ClsTables cls2;            // the same sector with the engine-2 table set (chunked tasks)
-  LongTables lng2;           // long rows, engine 2
-  int cls_engine = 0;        // engine the default (variant 0) class-major launches use: 0 or 2
-  int cls2_threads = 1024;   // CTA size of the engine-2 launches (512 / 768 / 896 / 1024)
   bool cls_default = false;  // variant 0 picks it
   int grid_limit = 0;        // > 0: cap on the CTAs of the persistent row kernels (leaves SMs to a concurrent kernel)
   int cls_shape = 0;         // 0: 1024 threads x 8 up-hop loads in flight, 1: 512 x 16, 2: 768 x 12
@@ -71,7 +67,7 @@ struct HubbardOp : cmpy_op_s {
                              // with 512 x 128 on the 4x4 sector, dn-only pass)
 
   ~HubbardOp() override {
-    up.release(); dn.release(); seg.release(); cls.release(); lng.release(); cls2.release(); lng2.release();
+    up.release(); dn.release(); seg.release(); cls.release(); lng.release();
     eng.release();
     cudaFree(d_hop); cudaFree(d_u);
   }
@@ -138,10 +134,8 @@ struct HubbardOp : cmpy_op_s {
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
     if (use_variant == 8 && !(lng.ok && UNI && aligned16 && !p.with_up && !LZ && (p.num_dn % 2 == 0)))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant not available for this call");
-    if (use_variant == 10 && !(lng2.ok && UNI && aligned16 && !p.with_up && !LZ && (p.num_dn % 2 == 0)))
-      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "long-row variant (engine 2) not available for this call");
-    if (use_variant == 9 && !(cls2.ok && UNI && aligned16))
-      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant (engine 2) not available for this call");
+    if (use_variant == 9 || use_variant == 10)
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "variants 9 / 10 (round-1 chunked-task engine) were removed");
     if (use_variant == 11 && !(eng.ok && UNI))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row-engine variant not available for this sector");
     if (p.acc_scale && !(eng.ok && UNI && !LZ && (use_variant == 0 || use_variant == 11)))
@@ -149,13 +143,10 @@ struct HubbardOp : cmpy_op_s {
     if (p.acc_scale) return launch_eng<LZ>(p, st);
     if (use_variant == 11 || (use_variant == 0 && eng.ok && UNI && (!p.with_up || eng_full)))
       return launch_eng<LZ>(p, st);
-    if (use_variant == 10) return launch_long(p, st, lng2, 2);
     if (use_variant == 8 || (use_variant == 0 && lng.ok && UNI && aligned16 && !p.with_up && !LZ &&
                              (p.num_dn % 2 == 0))) {
-      if (use_variant == 0 && cls_engine == 2 && lng2.ok) return launch_long(p, st, lng2, 2);
-      return launch_long(p, st, lng, 0);
+      return launch_long(p, st, lng);
     }
-    if (use_variant == 9) return launch_cls<LZ>(p, st, 2);
     if (use_variant >= 5 && use_variant <= 7 && !aligned16)
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant needs 16-byte aligned vectors");
     // default: the segment kernel for the full H.v (its up-hop gathers overlap the shared-memory
@@ -163,10 +154,9 @@ struct HubbardOp : cmpy_op_s {
     // hops (sharded operator: 2.1 vs 2.97 ms)
     if ((use_variant >= 5 && use_variant <= 7) ||
         (use_variant == 0 && cls.ok && cls_default && UNI && aligned16 && !p.with_up)) {
-      if (use_variant == 0 && cls_engine == 2 && cls2.ok) return launch_cls<LZ>(p, st, 2);
       const int saved = cls_shape;
       if (use_variant >= 5) cls_shape = use_variant - 5;
-      int rc = launch_cls<LZ>(p, st, 0);
+      int rc = launch_cls<LZ>(p, st);
       cls_shape = saved;
       return rc;
     }
@@ -299,32 +289,13 @@ struct HubbardOp : cmpy_op_s {
   }
 
   template <bool LZ>
-  int launch_cls(HubParams& p, cudaStream_t st, int eng) {
-    const ClsTables& T = eng == 2 ? cls2 : cls;
+  int launch_cls(HubParams& p, cudaStream_t st) {
+    const ClsTables& T = cls;
     ClsParams cp;
     cp.hp = p; cp.lay = T.lay; cp.blob = T.d_blob; cp.pair_seg = T.d_pair_seg; cp.e_dn_const = T.e_dn_const;
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
-    if (eng == 2) {  // engine 2: chunked tasks.  512 / 768-thread CTAs leave ptxas the registers to
-                     // keep several shared-memory loads of a hop list in flight per warp (at 64
-                     // registers it serialises every LDS -> DADD pair on one register)
-      if (cls2_threads == 512) {
-        if (!p.with_up) hub_cls_kernel<LZ, 512, 0, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
-        else hub_cls_kernel<LZ, 512, 16, false, false, 2><<<(int)g, 512, T.smem, st>>>(cp);
-      } else if (cls2_threads == 896) {
-        if (!p.with_up) hub_cls_kernel<LZ, 896, 0, false, false, 2><<<(int)g, 896, T.smem, st>>>(cp);
-        else hub_cls_kernel<LZ, 896, 10, false, false, 2><<<(int)g, 896, T.smem, st>>>(cp);
-      } else if (cls2_threads == 768) {
-        if (!p.with_up) hub_cls_kernel<LZ, 768, 0, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
-        else hub_cls_kernel<LZ, 768, 12, false, false, 2><<<(int)g, 768, T.smem, st>>>(cp);
-      } else {
-        if (!p.with_up) hub_cls_kernel<LZ, 1024, 0, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
-        else hub_cls_kernel<LZ, 1024, 8, false, false, 2><<<(int)g, 1024, T.smem, st>>>(cp);
-      }
-      KERNEL_CHECK();
-      return CMPY_OK;
-    }
     // (896 / 768 threads measured 2.36 / 2.43 ms vs 2.12 ms for 1024 on the 4x4 sector: issue-bound)
     if (!p.with_up) hub_cls_kernel<LZ, 1024, 0><<<(int)g, 1024, cls.smem, st>>>(cp);
     else if (cls_shape == 1) hub_cls_kernel<LZ, 512, 16><<<(int)g, 512, cls.smem, st>>>(cp);
@@ -335,7 +306,7 @@ struct HubbardOp : cmpy_op_s {
   }
 
   // dn-only pass over rows longer than shared memory: one launch per popcount of the top bits
-  int launch_long(HubParams& p, cudaStream_t st, LongTables& lt, int eng) {
+  int launch_long(HubParams& p, cudaStream_t st, LongTables& lt) {
     for (auto& S : lt.sets) {
       ClsParams cp;
       cp.hp = p; cp.lay = S.cls.lay; cp.blob = S.cls.d_blob; cp.pair_seg = S.shift ? S.cls.d_pair_seg1 : S.cls.d_pair_seg;
@@ -347,8 +318,7 @@ struct HubbardOp : cmpy_op_s {
       if (grid_limit > 0 && g > grid_limit) g = grid_limit;
       const i64 items = p.nrows * S.ntop;
       if (g > items) g = items;
-      if (eng == 2) hub_cls_kernel<false, 1024, 8, true, false, 2><<<(int)g, 1024, S.cls.smem, st>>>(cp);
-      else hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
+      hub_cls_kernel<false, 1024, 8, true><<<(int)g, 1024, S.cls.smem, st>>>(cp);
       KERNEL_CHECK();
     }
     return CMPY_OK;
@@ -364,18 +334,6 @@ struct HubbardOp : cmpy_op_s {
       int nb = 0;
       CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<false, 1024, 8, true>, 1024, S.cls.smem));
       if (nb < 1) { lng.release(); return CMPY_OK; }
-    }
-    // engine 2 (chunked tasks): same sub-row decomposition, its own table set
-    rc = build_long_tables(lng2, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, nullptr, 2);
-    if (rc) return rc;
-    if (lng2.ok) {
-      rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, true, false, 2>, smem_optin);
-      if (rc) return rc;
-      for (auto& S : lng2.sets) {
-        int nb = 0;
-        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<false, 1024, 8, true, false, 2>, 1024, S.cls.smem));
-        if (nb < 1) { lng2.release(); break; }
-      }
     }
     return CMPY_OK;
   }
@@ -398,34 +356,6 @@ struct HubbardOp : cmpy_op_s {
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8>, 1024, cls.smem));
     if (nb < 1) { cls.ok = false; return CMPY_OK; }
     cls_default = dn.num >= 2048;  // long rows: one CTA per SM anyway
-    // engine 2 (chunked tasks): its own table set, 1024-thread shapes
-    rc = build_cls_tables(cls2, num_sites, n_dn, dn.num, nbonds, s1, s2, sign_width, eps, smem_optin, 2);
-    if (rc) return rc;
-    if (cls2.ok) {
-      rc = raise_smem_limit(hub_cls_kernel<false, 1024, 8, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 8, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 1024, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 1024, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 896, 10, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 896, 10, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 896, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 896, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 12, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 768, 12, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 768, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 768, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 512, 16, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 512, 16, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<false, 512, 0, false, false, 2>, smem_optin);
-      if (!rc) rc = raise_smem_limit(hub_cls_kernel<true, 512, 0, false, false, 2>, smem_optin);
-      if (rc) return rc;
-      if (const char* e = getenv("CMPY_CLS2_THREADS")) {
-        const int t = atoi(e);
-        if (t == 512 || t == 768 || t == 896 || t == 1024) cls2_threads = t;
-      }
-      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hub_cls_kernel<true, 1024, 8, false, false, 2>, 1024, cls2.smem));
-      if (nb < 1) cls2.release();
-    }
     return CMPY_OK;
   }
 

@@ -123,8 +123,8 @@ int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_y_sl
  * 2 = shared-memory row staging with per-string tables, 3 / 4 = two-level segment kernel
  * with 512 / 1024 threads per CTA, 5-7 = class-major kernel (1024 x 8, 512 x 16, 768 x 12
  * threads x gathers in flight), 8 = long-row (more than 16 sites) class-major sub-row launches,
- * 9 / 10 = variants 5 / 8 with the chunked-task engine (CMPY_CLS_ENGINE=2 makes that engine the
- * one variant 0 picks for the class-major launches).  (Profiling / tests only.) */
+ * 11 = generation-3 row engine (hubbard_eng.cuh; the default of the row-slab entry point).
+ * (Profiling / tests only.) */
 int cmpy_hv_set_variant(cmpy_op_t op, int variant);
 /* trace(H) = sum of the diagonal.  ref: HamiltonOperator._trace cmpy/operators.py:641-646.
  * Synchronous. */

@@ -1,7 +1,7 @@
 // cls_emu.cu -- TEST INFRASTRUCTURE (not part of the product): runs the shared-memory phases of
 // the class-major H.v kernel (cmpy_b200/csrc/hubbard_cls.cuh) lane by lane on the CPU.
 //
-// The phase bodies (cls_phase_a/b = engine 0, cls2_phase_a/b = engine 2) are __host__ __device__;
+// The phase bodies (cls_phase_a/b) are __host__ __device__;
 // inside one phase every (warp, lane) only reads what the previous phase wrote and writes its
 // own slots, so executing the lanes one after the other is exactly what the barrier-separated
 // kernel computes.  Staging and un-staging follow the kernel's column-pair -> slot map
@@ -9,12 +9,10 @@
 // evaluation of (D + T_dn) x on one row (ref: cmpy/operators.py:305-527).
 //
 // Built by the test itself:  nvcc -O1 -std=c++17 -shared -Xcompiler -fPIC cls_emu.cu
-#define CMPY_EMU 1   // enables the load-address trace hook of the host-side cls_ld
 #include "../../cmpy_b200/csrc/hubbard_cls.cuh"
 #include "../../cmpy_b200/csrc/peer.cuh"
 #include <cmath>
 
-static long long g_wave_a[3], g_wave_b[3];   // wavefronts, ideal wavefronts, divergent tasks
 static int g_emu_shift = 0;
 extern "C" void emu_set_shift(int shift) { g_emu_shift = shift ? 1 : 0; }
 
@@ -24,54 +22,6 @@ static void run_phases(const ClsHost& H, const SpinDiag& sd, const std::vector<d
                        int nwarps) {
   const ClsLayout& L = H.lay;
   const unsigned char* tab = H.blob.data();
-  if (L.eng == 2) {
-    const uint32_t* task_a = reinterpret_cast<const uint32_t*>(tab + L.off_task_a);
-    const uint32_t* task_b = reinterpret_cast<const uint32_t*>(tab + L.off_task_b);
-    // Shared-memory wavefronts of the 8-byte loads of one warp-level task: the lanes of a warp run
-    // the same instruction sequence, so load i of every lane is one LDS.64; each half warp costs
-    // as many wavefronts as the most loaded 8-byte bank has distinct addresses.
-    std::vector<uintptr_t> tr[32];
-    auto account = [&](long long* acc) {
-      const size_t n = tr[0].size();
-      for (int l = 1; l < 32; ++l) if (tr[l].size() != n) { acc[2] += 1; return; }   // divergent: not counted
-      for (size_t i = 0; i < n; ++i)
-        for (int half = 0; half < 2; ++half) {
-          uintptr_t seen[16][16]; int cnt[16] = {0};
-          int worst = 0;
-          for (int l = 16 * half; l < 16 * half + 16; ++l) {
-            const uintptr_t a = tr[l][i];
-            const int bank = (int)((a >> 3) & 15);
-            bool dup = false;
-            for (int j = 0; j < cnt[bank]; ++j) dup |= seen[bank][j] == a;
-            if (!dup) seen[bank][cnt[bank]++] = a;
-            worst = cnt[bank] > worst ? cnt[bank] : worst;
-          }
-          acc[0] += worst;   // wavefronts
-          acc[1] += 1;       // ideal: one per half warp
-        }
-    };
-    for (int warp = 0; warp < nwarps; ++warp)   // the task loops of hub_cls_kernel<..., ENG = 2>
-      for (int pc = warp; pc < L.npieces; pc += nwarps)
-        for (int it = L.ptr_a[pc]; it < L.ptr_a[pc + 1]; ++it) {
-          for (int lane = 0; lane < 32; ++lane) {
-            tr[lane].clear(); g_cls_trace = &tr[lane];
-            cls2_task_a<SPIN>(L, sd, tab, xs.data(), ys.data(), task_a[it], ups, eu, u0, hop0, lane);
-          }
-          g_cls_trace = nullptr;
-          account(g_wave_a);
-        }
-    for (int warp = 0; warp < nwarps; ++warp)
-      for (int pc = warp; pc < L.npieces; pc += nwarps)
-        for (int it = L.ptr_b[pc]; it < L.ptr_b[pc + 1]; ++it) {
-          for (int lane = 0; lane < 32; ++lane) {
-            tr[lane].clear(); g_cls_trace = &tr[lane];
-            cls2_task_b(L, tab, xs.data(), ys.data(), task_b[it], hop0, lane);
-          }
-          g_cls_trace = nullptr;
-          account(g_wave_b);
-        }
-    return;
-  }
   // engine 0: the item headers of hub_cls_kernel, verbatim
   const uint16_t* item_a = reinterpret_cast<const uint16_t*>(tab + L.off_item_a);
   const uint16_t* item_b = reinterpret_cast<const uint16_t*>(tab + L.off_item_b);
@@ -123,7 +73,8 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
   const i64 num_dn = (i64)B[num_sites * BINOM_N + n_dn];
   ClsHost H;
   const double eps[1] = {eps0};
-  if (build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448, eng)) return 2;
+  if (eng != 0) return 2;   // (the round-1 chunked-task engine was removed)
+  if (build_cls_host(H, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448)) return 2;
   if (!H.ok) return 1;
   const ClsLayout& L = H.lay;
   SpinDiag sd;
@@ -166,7 +117,6 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
     if (slot[d] < 0 || slot[d] >= L.xs_elems) return 3;
     xs[slot[d]] = x_row[d];
   }
-  for (int i = 0; i < 3; ++i) g_wave_a[i] = g_wave_b[i] = 0;
   if (spin) run_phases<true>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
   else run_phases<false>(H, sd, xs, ys, ups, eu, u0, hop0, nwarps);
   for (i64 d = 0; d < num_dn; ++d) {
@@ -174,30 +124,8 @@ extern "C" int emu_cls_row(int num_sites, int n_dn, int nbonds, const int* s1, c
     if (std::isnan(y_row[d])) return 3;
   }
   if (info) {
-    info[0] = L.bytes; info[1] = (int)H.smem; info[2] = L.eng == 2 ? L.nta : L.na;
-    info[3] = L.eng == 2 ? L.ntb : L.nb; info[4] = L.nlh; info[5] = L.xs_elems;
-    if (L.eng == 2) {  // balance of the phase-A / phase-B pieces in (32-lane block x column) units
-      const uint32_t* tk[2] = {reinterpret_cast<const uint32_t*>(H.blob.data() + L.off_task_a),
-                               reinterpret_cast<const uint32_t*>(H.blob.data() + L.off_task_b)};
-      for (int ph = 0; ph < 2; ++ph) {
-        const uint16_t* ptr = ph ? L.ptr_b : L.ptr_a;
-        int mx = 0, tot = 0;
-        for (int pc = 0; pc < L.npieces; ++pc) {
-          int w = 0;
-          for (int it = ptr[pc]; it < ptr[pc + 1]; ++it) {
-            const int k = tk[ph][it] & 0xff, n = tk[ph][it] >> 16;
-            w += (((ph ? L.S[k] : L.H[k]) + 31) / 32) * n;
-          }
-          mx = w > mx ? w : mx; tot += w;
-        }
-        info[6 + 2 * ph] = mx; info[7 + 2 * ph] = tot;
-      }
-      info[10] = L.npieces;
-      // LDS.64 wavefronts of the phase bodies (x 1/1000), measured / conflict-free
-      info[11] = (int)(g_wave_a[0] / 1000); info[12] = (int)(g_wave_a[1] / 1000);
-      info[13] = (int)(g_wave_b[0] / 1000); info[14] = (int)(g_wave_b[1] / 1000);
-      info[15] = (int)(g_wave_a[2] + g_wave_b[2]);
-    }
+    info[0] = L.bytes; info[1] = (int)H.smem; info[2] = L.na;
+    info[3] = L.nb; info[4] = L.nlh; info[5] = L.xs_elems;
   }
   return 0;
 }
@@ -224,7 +152,7 @@ extern "C" int emu_long_row(int num_sites, int n_dn, int nbonds, const int* s1, 
   LongHost LH;
   std::vector<int> skipped;
   const double eps[1] = {0.0};
-  if (build_long_tables(dummy, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448, &skipped, eng, &LH))
+  if (build_long_tables(dummy, num_sites, n_dn, num_dn, nbonds, s1, s2, sign_width, eps, 232448, &skipped, &LH))
     return 2;
   if (LH.sets.empty()) return 1;
   SpinDiag sd;

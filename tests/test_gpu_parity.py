@@ -430,7 +430,7 @@ def test_hv_c4_full_vector_vs_oracle(cm):
     assert np.abs(got - ref).max() / scale < HV_RTOL
     # sample rows of every explicit kernel variant that supports this sector
     rows = [0, 6419, 12838]
-    for variant in (1, 4, 5, 9, 11):
+    for variant in (1, 4, 5, 11):
         h.set_variant(variant)
         yv = h.matvec(xd)
         for r0 in rows:

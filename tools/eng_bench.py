@@ -26,7 +26,7 @@ def run(name, L, nb, nu, nd, n=10):
     y = torch.empty_like(x); ref = torch.empty_like(x)
     out = {"config": name, "dim": dim}
     h.set_variant(4); h.apply_rows(x, 0, len(h.up_states), out=ref)
-    for v in (11, 5, 9, 4):
+    for v in (11, 5, 4):
         try:
             h.set_variant(v)
             ms = timeit(lambda: h.apply_rows(x, 0, len(h.up_states), out=y), n=n)
