@@ -582,7 +582,7 @@ def run_ours(args):
             "achieved_hbm_gbs_algorithmic": achieved * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": (getattr(hamop, "kernel_name", lambda: "hubbard H.v kernel")()
+                         "kernel": ("hub_seg_kernel<UNI, LZ=0, VEC2, 896> (default full H.v)"
                                     if world == 1 else "sharded step (per GPU): dn pass, push, up pass, pull"),
                          "algorithmic_bytes_per_launch": 16 * dim // world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -296,6 +296,9 @@ struct HubbardOp : cmpy_op_s {
     i64 g = sm_count;
     if (grid_limit > 0 && g > grid_limit) g = grid_limit;
     if (g > p.nrows) g = p.nrows;
+    // the up-hop offsets of this kernel are 32-bit element offsets relative to the row
+    if (p.with_up && (double)(up.num - 1) * (double)dn.num >= 2147483647.0)
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "class-major variant with up hops: sector too large for 32-bit row offsets");
     // (896 / 768 threads measured 2.36 / 2.43 ms vs 2.12 ms for 1024 on the 4x4 sector: issue-bound)
     if (!p.with_up) hub_cls_kernel<LZ, 1024, 0><<<(int)g, 1024, cls.smem, st>>>(cp);
     else if (cls_shape == 1) hub_cls_kernel<LZ, 512, 16><<<(int)g, 512, cls.smem, st>>>(cp);

@@ -861,6 +861,61 @@ def test_fourier_t2z_analytic(cm):
     assert np.abs(gz - ref).max() < 2e-5 * np.abs(ref).max()
 
 
+def test_fourier_t2z_two_poles_exact_piecewise_linear(cm):
+    """`fourier_t2z` pinned on a second analytic case.  (i) On a coarse, NON-uniform grid the result must
+    equal the exact integral of the piecewise-linear interpolant, written here in an independent algebraic
+    form (integration by parts, telescoped boundary terms) -- 1e-12; (ii) on a fine grid it must approach
+    the two-pole function a/(z - e1) + b/(z - e2).  gftool itself (cmpy/exactdiag.py:311-316) is absent."""
+    from cmpy_b200 import exactdiag as ed
+
+    a, b, e1, e2 = 0.3, 0.7, 0.7, -1.1
+    g = lambda t: -1j * (a * np.exp(-1j * e1 * t) + b * np.exp(-1j * e2 * t))
+    rng = np.random.default_rng(2)
+    t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.05, 0.4, 300))])
+    gt = g(t)
+    om = np.linspace(-2.5, 2.5, 41)
+    z, gz = ed.fourier_t2z(t, gt, om, eta=0.35)
+    iz = 1j * z[:, None]
+    e = np.exp(iz * t[None, :])
+    slope = (gt[1:] - gt[:-1]) / (t[1:] - t[:-1])
+    exact = (e[:, -1] * gt[-1] - e[:, 0] * gt[0]) / iz[:, 0] + (slope[None, :] * (e[:, 1:] - e[:, :-1])).sum(axis=1) / z ** 2
+    assert np.abs(gz - exact).max() < 1e-12 * max(1.0, np.abs(exact).max())
+    tf = np.linspace(0.0, 150.0, 60001)
+    z, gz = ed.fourier_t2z(tf, g(tf), om, delta=1e-9)
+    ref = a / (z - e1) + b / (z - e2)
+    assert np.abs(gz - ref).max() < 5e-5 * np.abs(ref).max()
+
+
+def test_expm_multiply_consumer_of_the_gpu_operator(cm):
+    """The reference's real-time path hands the Hamiltonian operator to `expm_multiply`
+    (cmpy/exactdiag.py:248-273 -> cmpy/linalg/expm_multiply.py:215-299, an adaptation of scipy's, which needs
+    `A.trace()`, scalar `*`, `A - mu I`, `A.H` and complex mat-vecs / mat-mats).  Here scipy's own
+    `expm_multiply` drives `SectorHamiltonOperator` (matrix-free, on the GPU) and must reproduce
+    G^>(t) from this package's spectral-measure evaluation (`gf_greater`) to 1e-8."""
+    import scipy.sparse.linalg as sla
+    from cmpy_b200 import exactdiag as ed
+    from cmpy_b200.matrix import EigenState
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.operators import CreationOperator
+
+    L = 6
+    model = HubbardModel(L, chain(L), inter=4.0, mu=2.0, hop=1.0)
+    sec = model.basis.get_sector(3, 3)
+    evals, evecs = np.linalg.eigh(model.hamiltonian(sector=sec))
+    gs = EigenState(float(evals[0]), evecs[:, 0].copy(), 3, 3)
+    start, stop, num = 0.0, 4.0, 21
+    times, gg = ed.gf_greater(model, gs, start, stop, num, 0, cm.UP)
+    sec_p1 = model.basis.upper_sector(3, 3, cm.UP)
+    phi = np.asarray(CreationOperator(sec, sec_p1, pos=0, sigma=cm.UP).matvec(gs.state), dtype=np.complex128)
+    hamop = model.hamilton_operator(sector=sec_p1)
+    assert abs(hamop.trace() - np.trace(model.hamiltonian(sector=sec_p1))) < 1e-9
+    a_op = -1j * hamop                       # scalar * operator keeps a LinearOperator with .H and matmat
+    tr = -1j * hamop.trace()
+    psi_t = sla.expm_multiply(a_op, phi, start=start, stop=stop, num=num, endpoint=True, traceA=tr)
+    ref = -1j * np.exp(1j * gs.energy * times) * (psi_t @ phi.conj())
+    assert np.abs(gg - ref).max() < 1e-8
+
+
 def test_matvec_batch_pipelined_host_vectors(cm):
     """Pipelined host batch (three streams, double buffering) == one blocking matvec per vector."""
     import torch

@@ -172,3 +172,39 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_np" not in src and "refshim" not in src, f
+
+
+def test_operator_spec_follows_the_generator_hook():
+    """A subclass that changes `_hamiltonian_data` without describing itself again must not inherit the
+    parent's matrix-free description (round-1 advisor finding; reference hook: cmpy/models/abc.py:238-256)."""
+    from cmpy_b200.models import HubbardModel
+
+    class Extended(HubbardModel):
+        def _hamiltonian_data(self, up_states, dn_states):
+            yield from super()._hamiltonian_data(up_states, dn_states)
+            yield 0, 0, 1.0
+
+    class Redescribed(Extended):
+        def _operator_spec(self):
+            return HubbardModel._operator_spec(self)
+
+    nb = [[0, 1], [1, 2]]
+    base = HubbardModel(3, nb, inter=2.0, mu=1.0, hop=1.0)
+    assert base._trusted_spec() is not None
+    assert Extended(3, nb, inter=2.0, mu=1.0, hop=1.0)._trusted_spec() is None
+    assert Redescribed(3, nb, inter=2.0, mu=1.0, hop=1.0)._trusted_spec() is not None
+    # the parameter container still behaves like the reference's (cmpy/models/abc.py:21-133)
+    assert base.inter == 2.0 and base["inter"] == 2.0
+    base.inter = 3.0
+    assert base["inter"] == 3.0 and "inter" in base.params
+    assert str(base).startswith("HubbardModel(") and "U=3.0" in base.pformat()
+    from cmpy_b200.models.abc import ModelParameters
+
+    mp = ModelParameters(a=1.0, b=2)
+    mp.rename_param("a", "c")
+    assert mp.c == 1.0 and "a" not in mp and list(mp) == ["b", "c"]
+    assert mp.key(decimals=1) == "b=2.0; c=1.0" and mp.json() == '{"b": 2, "c": 1.0}'
+    mp.delete_param("b")
+    assert len(mp) == 1 and mp.pformat() == "c=1.0"
+    with pytest.raises(AttributeError):
+        mp.nope
