@@ -466,6 +466,10 @@ __global__ void __launch_bounds__(NT, 1) hub_cls_kernel(ClsParams cp) {
         }
         if (v0) dot += (s1 * x0) * w0;
         if (v1) dot += (s1 * x1) * w1;
+      } else if (p.acc_scale) {   // y = c1 * (H x) + c2 * y (sharded Lanczos recurrence, device scalars)
+        const double c1 = p.acc_scale[0], c2 = p.acc_scale[1];
+        w0 = c1 * w0 + (v0 ? c2 * yr[d] : 0.0);
+        w1 = c1 * w1 + (v1 ? c2 * yr[d + 1] : 0.0);
       } else if (p.accumulate) {
         if (v0) w0 += yr[d];
         if (v1) w1 += yr[d + 1];

@@ -138,9 +138,15 @@ struct HubbardOp : cmpy_op_s {
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "variants 9 / 10 (round-1 chunked-task engine) were removed");
     if (use_variant == 11 && !(eng.ok && UNI))
       return cmpy_fail(CMPY_ERR_UNSUPPORTED, "row-engine variant not available for this sector");
-    if (p.acc_scale && !(eng.ok && UNI && !LZ && (use_variant == 0 || use_variant == 11)))
-      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "scaled accumulation needs the row engine");
-    if (p.acc_scale) return launch_eng<LZ>(p, st);
+    if (p.acc_scale) {   // scaled accumulation: row engine, long-row or plain class-major kernel (dn pass only)
+      const bool a16 = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) & 15) == 0;
+      if (LZ || p.with_up || !UNI || use_variant != 0)
+        return cmpy_fail(CMPY_ERR_UNSUPPORTED, "scaled accumulation: dn pass of a uniform model only");
+      if (eng.ok) return launch_eng<LZ>(p, st);
+      if (lng.ok && a16 && (p.num_dn % 2 == 0)) return launch_long(p, st, lng);
+      if (cls.ok && a16) return launch_cls<LZ>(p, st);
+      return cmpy_fail(CMPY_ERR_UNSUPPORTED, "scaled accumulation needs the row engine or the class-major kernel");
+    }
     if (use_variant == 11 || (use_variant == 0 && eng.ok && UNI && (!p.with_up || eng_full)))
       return launch_eng<LZ>(p, st);
     if (use_variant == 8 || (use_variant == 0 && lng.ok && UNI && aligned16 && !p.with_up && !LZ &&

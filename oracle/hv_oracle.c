@@ -136,3 +136,72 @@ int orc_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ---- Heisenberg (spin) sector ------------------------------------------------------------------ */
+/* binomials for the combinadic rank: position of a state in the ascending list of N-bit integers of
+ * fixed popcount == states.index(s2) in HeisenbergModel._hamiltonian_data
+ * (cmpy/models/heisenberg.py:38, states from SpinBasis.get_states, cmpy/basis.py:748-774) */
+static int64_t g_binom[65][65];
+static void binom_init(void) {
+  static int done = 0;
+  if (done) return;
+  for (int n = 0; n < 65; ++n)
+    for (int k = 0; k < 65; ++k)
+      g_binom[n][k] = (k == 0) ? 1 : (n == 0 ? 0 : g_binom[n - 1][k - 1] + g_binom[n - 1][k]);
+  done = 1;
+}
+static int64_t colex_rank64(uint64_t s) {
+  int64_t r = 0;
+  int k = 0;
+  while (s) {
+    int p = __builtin_ctzll(s);
+    s &= s - 1;
+    r += g_binom[p][++k];
+  }
+  return r;
+}
+static uint64_t colex_unrank64(int64_t idx, int n, int num_sites) {
+  uint64_t s = 0;
+  int p = num_sites;
+  for (int k = n; k >= 1; --k) {
+    do { --p; } while (g_binom[p][k] > idx);
+    s |= 1ull << p;
+    idx -= g_binom[p][k];
+  }
+  return s;
+}
+
+/* y[r] = (H x)[i0 + r], r < count, for the sector of popcount n_up of an N-site Heisenberg model:
+ * HeisenbergModel._hamiltonian_data (cmpy/models/heisenberg.py:19-40) applied matrix-free, the loops
+ * pos1 in range(N), pos2 in neighbors(pos1) (directed pairs, nbr_ptr / nbr_idx) in the reference's
+ * order; H is symmetric, so the gather below equals HamiltonOperator._matvec (cmpy/operators.py:626-630). */
+void orc_heisenberg_hv_range(int num_sites, int n_up, const int32_t* nbr_ptr, const int32_t* nbr_idx,
+                             double j, double jz, const double* x, double* y, int64_t i0, int64_t count,
+                             int nthreads) {
+  binom_init();
+  const double factor = 0.25;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static, 4096)
+#endif
+  for (int64_t r = 0; r < count; ++r) {
+    const int64_t i = i0 + r;
+    const uint64_t s1 = colex_unrank64(i, n_up, num_sites);
+    const double xi = x[i];
+    double acc = 0.0;
+    for (int pos1 = 0; pos1 < num_sites; ++pos1)
+      for (int32_t q = nbr_ptr[pos1]; q < nbr_ptr[pos1 + 1]; ++q) {
+        const int pos2 = nbr_idx[q];
+        const int b1 = (int)((s1 >> pos1) & 1ull), b2 = (int)((s1 >> pos2) & 1ull);
+        const double sign = (b1 == b2) ? 1.0 : -1.0;
+        acc += (sign * factor * jz) * xi;
+        if (b1 != b2) acc += (factor * j / 2) * x[colex_rank64(s1 ^ (1ull << pos1) ^ (1ull << pos2))];
+      }
+    y[r] = acc;
+  }
+}
+
+int64_t orc_binomial(int n, int k) {
+  binom_init();
+  return (n < 0 || n > 64 || k < 0 || k > 64) ? 0 : g_binom[n][k];
+}

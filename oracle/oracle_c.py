@@ -42,6 +42,11 @@ def lib():
             POINTER(c_double), POINTER(c_double), POINTER(c_int32), POINTER(c_int8), POINTER(c_int32),
             POINTER(c_int8), POINTER(c_double), POINTER(c_double), c_int64, c_int64, c_int]
         _lib.orc_max_threads.restype = c_int
+        _lib.orc_heisenberg_hv_range.restype = None
+        _lib.orc_heisenberg_hv_range.argtypes = [c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_double, c_double,
+                                                 POINTER(c_double), POINTER(c_double), c_int64, c_int64, c_int]
+        _lib.orc_binomial.restype = c_int64
+        _lib.orc_binomial.argtypes = [c_int, c_int]
     return _lib
 
 
@@ -110,3 +115,33 @@ def hubbard_oracle(num_sites, n_up, n_dn, neighbors, inter, eps, hop, width=None
     dn = enumerate_states(num_sites, n_dn)
     return HubbardOracle(num_sites, up, dn, bonds, np.full(len(bonds), hop), np.full(num_sites, eps),
                          np.full(num_sites, inter), num_sites if width is None else width)
+
+
+class HeisenbergOracle:
+    """Matrix-free H.v of `HeisenbergModel._hamiltonian_data` (cmpy/models/heisenberg.py:19-40) on the sector
+    of `n_up` up spins, any contiguous range of rows; `neighbor_lists[pos1]` = the reference's
+    `latt.neighbors(pos1)` (directed pairs)."""
+
+    def __init__(self, num_sites, n_up, neighbor_lists, j=1.0, jz=1.0):
+        self.num_sites, self.n_up, self.j, self.jz = int(num_sites), int(n_up), float(j), float(jz)
+        ptr = [0]
+        idx = []
+        for pos1 in range(self.num_sites):
+            idx.extend(int(p) for p in neighbor_lists[pos1])
+            ptr.append(len(idx))
+        self.ptr = np.asarray(ptr, dtype=np.int32)
+        self.idx = np.asarray(idx if idx else [0], dtype=np.int32)
+        self.size = int(lib().orc_binomial(self.num_sites, self.n_up))
+
+    def matvec_range(self, x, i0=0, count=None, nthreads=0):
+        count = self.size - i0 if count is None else count
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.size and 0 <= i0 and i0 + count <= self.size
+        y = np.empty(count, dtype=np.float64)
+        lib().orc_heisenberg_hv_range(self.num_sites, self.n_up, _p(self.ptr, c_int32), _p(self.idx, c_int32),
+                                      self.j, self.jz, _p(x, c_double), _p(y, c_double), int(i0), int(count),
+                                      int(nthreads))
+        return y
+
+    def matvec(self, x, nthreads=0):
+        return self.matvec_range(x, 0, None, nthreads)

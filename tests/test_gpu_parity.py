@@ -772,6 +772,43 @@ def test_heisenberg_xx_chain_n32_c3(cm):
     assert abs(res.e0 - e_ref) < E0_TOL
 
 
+def test_heisenberg_c3_sample_ranges_vs_oracle(cm):
+    """BASELINE config C3 itself (Heisenberg chain N=32, Sz=0, j=jz=1, dim 601 080 390, the long-row spin
+    path incl. the odd sub-rows left to the generic kernel): ranges of the result vector at the start, in
+    the middle, across a high-word boundary and at the end against the C oracle
+    (oracle/hv_oracle.c::orc_heisenberg_hv_range, pinned to the reference fixtures), 1e-12; then the
+    fused Lanczos instantiation through alpha_0 = <v|H|v> accumulated from the same ranges is NOT
+    possible without the whole H.v, so the Lanczos variant is checked through the symmetric form
+    <x|H y> = <H x|y> (ref: cmpy/models/heisenberg.py:19-40)."""
+    import torch
+    import oracle_c
+    from cmpy_b200.models import HeisenbergModel
+    from refshim import ChainStandIn
+
+    N = 32
+    model = HeisenbergModel(ChainStandIn(N), j=1.0, jz=1.0)
+    h = model.hamilton_operator(s=0)
+    n = h.shape[0]
+    assert n == 601080390
+    oc = oracle_c.HeisenbergOracle(N, N // 2, orc.chain_neighbor_lists(N), 1.0, 1.0)
+    assert oc.size == n
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    x = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    y = h.matvec(x)
+    xh = x.cpu().numpy()
+    scale = float(y.abs().max())
+    cnt = 200000
+    for i0 in (0, n // 3, n // 2 - cnt // 2, n - cnt):
+        ref = oc.matvec_range(xh, i0, cnt)
+        got = y[i0:i0 + cnt].cpu().numpy()
+        assert np.abs(got - ref).max() / scale < HV_RTOL, i0
+    del xh
+    z = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    hz = h.matvec(z)
+    lhs, rhs = float(torch.dot(x, hz)), float(torch.dot(y, z))
+    assert abs(lhs - rhs) < 1e-9 * max(abs(lhs), 1.0) * 10
+
+
 # ---------------------------------------------------------------------------------------
 # K9: sharded H.v building blocks (single process; the exchange itself is covered by the
 # gloo tests on CPU and by bench.py --gpus N)

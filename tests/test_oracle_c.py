@@ -36,3 +36,25 @@ def test_c_siam_signless(golden):
     x = np.cos(0.37 * np.arange(36))
     ref = golden["siam4_22_hv"]
     assert np.abs(o.matvec(x) - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("N", [4, 6, 8, 10])
+def test_c_heisenberg_golden(golden, N):
+    """C restatement of the Heisenberg H.v against the H.v produced by the unmodified reference."""
+    o = orcc.HeisenbergOracle(N, N // 2, orc.chain_neighbor_lists(N), 1.0, 1.0)
+    x = np.cos(0.37 * np.arange(o.size))
+    ref = golden[f"heis_chain{N}_s0_hv"]
+    assert np.abs(o.matvec(x) - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert_array_equal(o.matvec_range(x, 3, 2, nthreads=1), o.matvec(x)[3:5])
+
+
+@pytest.mark.parametrize("N,n_up,periodic,j,jz", [(12, 6, False, 0.9, 1.1), (11, 4, True, 1.0, -0.4), (14, 7, True, 1.3, 0.0)])
+def test_c_heisenberg_vs_numpy(N, n_up, periodic, j, jz):
+    nbl = orc.chain_neighbor_lists(N, periodic)
+    st = orc.enumerate_states(N, n_up)
+    r, c, v = orc.heisenberg_triplets(st, nbl, j, jz)
+    x = np.random.default_rng(1).standard_normal(len(st))
+    ref = orc.coo_matvec(len(st), r, c, v, x)
+    o = orcc.HeisenbergOracle(N, n_up, nbl, j, jz)
+    assert o.size == len(st)
+    assert np.abs(o.matvec(x) - ref).max() <= 1e-13 * np.abs(ref).max()

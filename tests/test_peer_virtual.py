@@ -117,6 +117,7 @@ def test_sharded_sequence_with_virtual_ranks(L, nu_f, nd_f, nbfn, world):
     (8, 4, 4, lambda: orc.chain_neighbors(8)),
     (10, 5, 5, lambda: orc.square_neighbors(2, 5)),
     (12, 6, 6, lambda: orc.square_neighbors(4, 3)),
+    (18, 1, 9, lambda: orc.chain_neighbors(18)),     # rows of more than 16 sites: long-row kernel (the C5 path)
 ])
 def test_c_dist_calls_world1(L, nu_f, nd_f, nbfn):
     """cmpy_dist_create / cmpy_hv_apply_sharded / cmpy_dist_allreduce_sum / cmpy_lanczos_sharded with a
@@ -174,7 +175,7 @@ def test_c_dist_calls_world1(L, nu_f, nd_f, nbfn):
                                       beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                       ctypes.byref(nit), ctypes.byref(e0), _lib.stream_ptr())
         if rc == _lib.CMPY_ERR_UNSUPPORTED:   # sector outside the row engine (e.g. more than 4 LH bonds):
-            assert b"row engine" in lib.cmpy_last_error()   # the Python recurrence is the documented fallback
+            assert b"scaled accumulation" in lib.cmpy_last_error()   # the Python recurrence is the documented fallback
             return
         assert rc in (_lib.CMPY_OK, _lib.CMPY_ERR_NOT_CONVERGED), lib.cmpy_last_error()
         m = min(nit.value, res.nit, 40)
