@@ -10,7 +10,7 @@ from cmpy_b200.models import HubbardModel, HeisenbergModel
 from cmpy_b200.exactdiag import lanczos_run, gf_continued_fraction
 from cmpy_b200 import _lib
 
-PEAK = 6466.1
+PEAK = 6541.1
 which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
 
 def time_hv(h, n=20):
