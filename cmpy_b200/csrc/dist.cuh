@@ -154,6 +154,7 @@ struct cmpy_dist_s {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int push_sms = 32;
+  int pull_rows = 32;             // rows per tile of the pull transpose (remote runs of 8 * pull_rows bytes)
   ~cmpy_dist_s() {
     cudaFree(d_epoch); cudaFree(d_part); cudaFree(d_coef); cudaFree(d_sum);
     if (side) cudaStreamDestroy(side);
@@ -209,9 +210,20 @@ struct cmpy_dist_s {
     rc = barrier(st);       // every YT slab is complete
     if (rc) return rc;
     if (nr > 0 && num_dn > 0) {
-      const i64 ntiles = ((nr + 31) / 32) * ((num_dn + 31) / 32);
-      const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-      peer_transpose_kernel<true, 32><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, scaled ? d_coef : nullptr);
+      const double* sc = scaled ? d_coef : nullptr;
+      if (pull_rows == 64) {
+        const i64 ntiles = ((nr + 63) / 64) * ((num_dn + 31) / 32);
+        const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+        peer_transpose_kernel<true, 64><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
+      } else if (pull_rows == 128) {
+        const i64 ntiles = ((nr + 127) / 128) * ((num_dn + 31) / 32);
+        const int g = (int)(ntiles < 148 * 6 ? ntiles : 148 * 6);
+        peer_transpose_kernel<true, 128><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
+      } else {
+        const i64 ntiles = ((nr + 31) / 32) * ((num_dn + 31) / 32);
+        const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+        peer_transpose_kernel<true, 32><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
+      }
       KERNEL_CHECK();
     }
     return CMPY_OK;
@@ -260,6 +272,7 @@ static int dist_create_impl(cmpy_op_s* op_main, cmpy_op_s* op_t, int world, int 
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete d; return cmpy_fail(CMPY_ERR_CUDA, std::string("dist_create: ") + cudaGetErrorString(e)); }
   if (const char* s = getenv("CMPY_PUSH_SMS")) d->push_sms = atoi(s);
+  if (const char* s = getenv("CMPY_PULL_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 128) d->pull_rows = v; }
   *out = d;
   return CMPY_OK;
 }

@@ -426,6 +426,10 @@ __global__ void __launch_bounds__(NT, 1) hub_eng_kernel(const __grid_constant__ 
         if (l2) eng_cp_async8(dst + 512u, src + 64);
       }
     }
+    if (row + gridDim.x < p.nrows) {   // pull the next row of this CTA into L2 while this one is processed
+      const char* nxt = reinterpret_cast<const char*>(xr + (i64)gridDim.x * nd);
+      for (int b = tid * 128; b < (int)(nd * 8); b += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + b));
+    }
     if (WITH_UP) {
       const int cu = p.with_up ? (int)p.cnt_up[u] : 0;
       E.cu = cu;
