@@ -380,6 +380,18 @@ class ShardedHubbardOperator:
         return self._pinned_out.clone()
 
 
+def _sharded_matvec_batch(self, xs, outs=None):
+    """Pipelined host batch on the local slabs (H2D of slab i+1 || sharded H.v of slab i || D2H of result
+    i-1), the sharded counterpart of ``HamiltonOperator.matvec_batch``; collective: every rank passes the
+    same number of slabs."""
+    from .operators import pipelined_host_batch
+
+    return pipelined_host_batch(self, self.local_size, lambda dx, dy: self.apply_local(dx, out=dy), xs, outs)
+
+
+ShardedHubbardOperator.matvec_batch = _sharded_matvec_batch
+
+
 def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, seed=0, callback=None,
                     want_vector=False, resid_tol=0.0):
     """Two-vector Lanczos on an up-string-sharded operator: every rank holds its slab of the two

@@ -228,6 +228,54 @@ class LinearOperator(sla.LinearOperator, abc.ABC):
         return self._decorate(super().__rmul__(x), x)
 
 
+def pipelined_host_batch(owner, n, apply_fn, xs, outs=None):
+    """Shared by the single-GPU and the sharded operator: ``apply_fn(dx, dy)`` computes dy = H dx on the
+    current stream for device vectors of ``n`` elements; host vectors stream through two device buffers
+    on three streams (H2D of vector i+1 || H.v of vector i || D2H of result i-1)."""
+    torch = _lib.require_cuda()
+    dev = _lib.device()
+    st = getattr(owner, "_batch_state", None)
+    if st is None:
+        st = dict(h2d=torch.cuda.Stream(), comp=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
+                  dx=[torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(2)],
+                  dy=[torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(2)], outs=None)
+        owner._batch_state = st
+    if outs is None:
+        if st["outs"] is None:
+            st["outs"] = [torch.empty(max(n, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+        outs = st["outs"]
+    cur = torch.cuda.current_stream()
+    for s_ in (st["h2d"], st["comp"], st["d2h"]):
+        s_.wait_stream(cur)
+    comp_done = [None, None]
+    d2h_done = [None, None]
+    results = []
+    for i, x in enumerate(xs):
+        if x.is_cuda or x.dtype != torch.float64 or x.numel() != n:
+            raise TypeError("matvec_batch expects CPU float64 tensors of the operator's (local) size")
+        b = i & 1
+        if comp_done[b] is not None:
+            st["h2d"].wait_event(comp_done[b])        # dx[b] was consumed by H.v i-2
+        with torch.cuda.stream(st["h2d"]):
+            st["dx"][b][:n].copy_(x.view(-1), non_blocking=True)
+            ev_in = torch.cuda.Event(); ev_in.record()
+        st["comp"].wait_event(ev_in)
+        if d2h_done[b] is not None:
+            st["comp"].wait_event(d2h_done[b])         # dy[b] was copied out (result i-2)
+        with torch.cuda.stream(st["comp"]):
+            apply_fn(st["dx"][b][:n], st["dy"][b][:n])
+            comp_done[b] = torch.cuda.Event(); comp_done[b].record()
+        st["d2h"].wait_event(comp_done[b])
+        out = outs[i % len(outs)]
+        with torch.cuda.stream(st["d2h"]):
+            out.view(-1)[:n].copy_(st["dy"][b][:n], non_blocking=True)
+            d2h_done[b] = torch.cuda.Event(); d2h_done[b].record()
+        results.append(out)
+    for s_ in (st["h2d"], st["comp"], st["d2h"]):
+        s_.synchronize()
+    return results
+
+
 class _DeviceOperatorMixin:
     """Shared GPU plumbing: the C handle, host<->device staging, Lanczos entry."""
 
@@ -344,49 +392,7 @@ class _DeviceOperatorMixin:
         ``xs``: CPU float64 tensors (pinned memory for full speed).  ``outs``: optional CPU tensors
         receiving the results (cycled if shorter than ``xs``); default two pinned buffers, i.e. only
         the last two results stay valid.  Returns the list of output tensors, one per input."""
-        torch = _lib.require_cuda()
-        n = self.shape[0]
-        dev = _lib.device()
-        st = getattr(self, "_batch_state", None)
-        if st is None:
-            st = dict(h2d=torch.cuda.Stream(), comp=torch.cuda.Stream(), d2h=torch.cuda.Stream(),
-                      dx=[torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)],
-                      dy=[torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2)], outs=None)
-            self._batch_state = st
-        if outs is None:
-            if st["outs"] is None:
-                st["outs"] = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
-            outs = st["outs"]
-        cur = torch.cuda.current_stream()
-        for s_ in (st["h2d"], st["comp"], st["d2h"]):
-            s_.wait_stream(cur)
-        comp_done = [None, None]
-        d2h_done = [None, None]
-        results = []
-        for i, x in enumerate(xs):
-            if x.is_cuda or x.dtype != torch.float64 or x.numel() != n:
-                raise TypeError("matvec_batch expects CPU float64 tensors of the operator's size")
-            b = i & 1
-            if comp_done[b] is not None:
-                st["h2d"].wait_event(comp_done[b])        # dx[b] was consumed by H.v i-2
-            with torch.cuda.stream(st["h2d"]):
-                st["dx"][b].copy_(x.view(-1), non_blocking=True)
-                ev_in = torch.cuda.Event(); ev_in.record()
-            st["comp"].wait_event(ev_in)
-            if d2h_done[b] is not None:
-                st["comp"].wait_event(d2h_done[b])         # dy[b] was copied out (result i-2)
-            with torch.cuda.stream(st["comp"]):
-                self.apply(st["dx"][b], out=st["dy"][b])
-                comp_done[b] = torch.cuda.Event(); comp_done[b].record()
-            st["d2h"].wait_event(comp_done[b])
-            out = outs[i % len(outs)]
-            with torch.cuda.stream(st["d2h"]):
-                out.view(-1).copy_(st["dy"][b], non_blocking=True)
-                d2h_done[b] = torch.cuda.Event(); d2h_done[b].record()
-            results.append(out)
-        for s_ in (st["h2d"], st["comp"], st["d2h"]):
-            s_.synchronize()
-        return results
+        return pipelined_host_batch(self, self.shape[0], lambda dx, dy: self.apply(dx, out=dy), xs, outs)
 
     def diagonal(self) -> np.ndarray:
         torch = _lib.require_cuda()

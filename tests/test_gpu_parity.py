@@ -829,6 +829,12 @@ def test_sharded_operator_world1_matches_single(cm):
         assert float((got - ref).abs().max()) < 1e-12 * float(ref.abs().max())
         yh = sh.matvec(x.cpu().pin_memory())
         assert not yh.is_cuda and float((yh - ref.cpu()).abs().max()) < 1e-12 * float(ref.abs().max())
+        # pipelined host batch of local slabs (the e2e call of bench.py at every N)
+        xs = [x.cpu().pin_memory(), (2.0 * x).cpu().pin_memory(), (-x).cpu().pin_memory()]
+        outs = [torch.empty(h.shape[0], dtype=torch.float64).pin_memory() for _ in range(3)]
+        res = sh.matvec_batch(xs, outs)
+        for f, r in zip((1.0, 2.0, -1.0), res):
+            assert float((r - f * ref.cpu()).abs().max()) < 1e-12 * float(ref.abs().max())
 
 
 def test_transpose_copy2d_kernels(cm):
