@@ -562,8 +562,7 @@ def run_ours(args):
         barrier()
         lanczos = {"seconds": time.perf_counter() - t0, "iterations": int(nits), "e0": float(e0s),
                    "converged": bool(convs), "tol": 1e-10,
-                   "path": ("cmpy_lanczos_sharded (C call, device-side all-reduces)"
-                            if getattr(hamop, "_cdist", None) is not None else "python recurrence")}
+                   "path": getattr(hamop, "last_lanczos_path", "python")}
 
     clocks = sampler.stop() if sampler is not None else None
 

@@ -40,20 +40,29 @@ __device__ __forceinline__ unsigned long long dist_ld_acquire(const unsigned lon
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// thread q < world: tell rank q that this rank reached `ep`, wait until rank q has told us the same
-__device__ __forceinline__ void dist_handshake(const CtlTable& ct, unsigned long long ep, int q) {
+// thread q < world: tell rank q that this rank reached `ep`, wait until rank q has told us the same.
+// The wait gives up after ~20 s of SM clocks (a peer that died must not hang this GPU for good); the
+// epoch counter then stops advancing, which the host sees as CMPY_ERR_CUDA at its next check.
+#define DIST_SPIN_LIMIT 40000000000ll
+__device__ __forceinline__ bool dist_handshake(const CtlTable& ct, unsigned long long ep, int q) {
   dist_st_release(&ct.ctl[q]->flag[ct.rank], ep);
   const unsigned long long* mine = &ct.ctl[ct.rank]->flag[q];
-  while (dist_ld_acquire(mine) < ep) { }
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while (dist_ld_acquire(mine) < ep) {
+    if ((++spins & 1023u) == 0u && clock64() - t0 > DIST_SPIN_LIMIT) return false;
+  }
+  return true;
 }
 
 // epoch: device counter of this rank (every rank runs the same sequence of barrier / all-reduce kernels)
 __global__ void __launch_bounds__(32) dist_barrier_kernel(CtlTable ct, unsigned long long* epoch) {
   const unsigned long long ep = *epoch + 1;
   __syncwarp();
-  if ((int)threadIdx.x < ct.world) dist_handshake(ct, ep, threadIdx.x);
-  __syncwarp();
-  if (threadIdx.x == 0) *epoch = ep;
+  bool ok = true;
+  if ((int)threadIdx.x < ct.world) ok = dist_handshake(ct, ep, threadIdx.x);
+  ok = __all_sync(0xffffffffu, ok);
+  if (threadIdx.x == 0 && ok) *epoch = ep;
 }
 
 // mode 0: out[v] = sum_q partial_q[v]
@@ -70,10 +79,10 @@ __global__ void __launch_bounds__(32) dist_allreduce_kernel(CtlTable ct, unsigne
 #pragma unroll
     for (int v = 0; v < DIST_NVAL; ++v) ct.ctl[q]->slot[par][ct.rank][v] = partial[v];
     __threadfence_system();
-    dist_handshake(ct, ep, q);
+    if (!dist_handshake(ct, ep, q)) partial = nullptr;   // timed out: flagged below
   }
-  __syncwarp();
-  if (threadIdx.x == 0) {
+  const bool ok = __all_sync(0xffffffffu, partial != nullptr);
+  if (threadIdx.x == 0 && ok) {
     double s[DIST_NVAL];
 #pragma unroll
     for (int v = 0; v < DIST_NVAL; ++v) s[v] = 0.0;

@@ -411,8 +411,11 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
 
     if (getattr(op, "_cdist", None) is not None and callback is None and not want_vector and resid_tol <= 0):
         res = _lanczos_sharded_c(op, v0_local, maxit, tol, check_every, seed)
+        op.last_lanczos_path = "c (cmpy_lanczos_sharded)" if res is not None else "python"
         if res is not None:
             return res
+    else:
+        op.last_lanczos_path = "python"
     dist = op.dist
     multi = dist.is_initialized() and op.world > 1
 

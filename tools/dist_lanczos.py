@@ -62,8 +62,7 @@ if rank == 0:
     out = dict(workload=wl, L=L, U=U, dim=dim, n_gpus=world, exchange=op.exchange, build_s=t_build,
                hv_ms=hv_ms, hv_algorithmic_gbs_per_gpu=16.0 * dim / world / (hv_ms * 1e-3) / 1e9,
                nvlink_out_gbs_per_gpu=p.bytes_out_per_hv() / (hv_ms * 1e-3) / 1e9,
-               lanczos_path=("python" if (verbose or getattr(op, "_cdist", None) is None or L > 16)
-                             else "c (cmpy_lanczos_sharded)"),
+               lanczos_path=getattr(op, "last_lanczos_path", "python"),
                lanczos_s=t_lz, iterations=nit, converged=bool(conv), e0=e0,
                ms_per_iteration=1e3 * t_lz / max(nit, 1), max_mem_gb=mem, phases_ms=phases)
     if U == 0.0:  # free fermions: E0 = 2 * sum of the n lowest levels of the hopping matrix (mu = 0)
