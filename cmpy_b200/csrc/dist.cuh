@@ -41,8 +41,9 @@ __device__ __forceinline__ unsigned long long dist_ld_acquire(const unsigned lon
   return v;
 }
 // thread q < world: tell rank q that this rank reached `ep`, wait until rank q has told us the same.
-// The wait gives up after ~20 s of SM clocks (a peer that died must not hang this GPU for good); the
-// epoch counter then stops advancing, which the host sees as CMPY_ERR_CUDA at its next check.
+// The wait gives up after ~20 s of SM clocks: a peer that died must not hang this GPU for good.  After a
+// give-up the epoch counter stops advancing and later results are meaningless (the process is expected to
+// fail on its dead peer anyway; the parity checks of bench.py / the tests would flag a silent case).
 #define DIST_SPIN_LIMIT 40000000000ll
 __device__ __forceinline__ bool dist_handshake(const CtlTable& ct, unsigned long long ep, int q) {
   dist_st_release(&ct.ctl[q]->flag[ct.rank], ep);
