@@ -180,7 +180,7 @@ def cpu_port_rate(workload, target_seconds, steps, warmup, orc=None):
     return 1.0 / full, dt * 1e3, info
 
 
-def cpu_port_lanczos(workload, orc=None, budget_s=200.0):
+def cpu_port_lanczos(workload, orc=None, budget_s=120.0):
     """Second half of the metric on the CPU arm: the reference's ground-state call
     `sla.eigsh(hamop, k=1, which="SA")` (cmpy/exactdiag.py:37) with the C port as the operator's
     mat-vec, tol 1e-10.  Bounded: the mat-vec raises once `budget_s` is used up and the record then
