@@ -46,41 +46,40 @@ def compute_self_energy(z, siam, ref=False):
     return self_energy(impurity_gf0(z, siam), compute_impurity_gf(z, siam, ref=ref))
 
 
+def _next_hybridization(z, siam, v, t, mixing, vthresh, ref):
+    """One self-consistency step: solve the impurity problem at hybridisation ``v``, return the mixed
+    new hybridisation sqrt(Z) t and the quasiparticle weight Z (reference: twosite.py:127-139)."""
+    siam.update_hybridization(v)
+    sigma = compute_self_energy(z, siam, ref=ref)
+    weight = quasiparticle_weight(z.real, sigma, thresh=vthresh)
+    return mix_values(v, np.sqrt(weight * t * t), mixing=mixing), weight
+
+
 def twosite_dmft_half_filling(z, u, t=1.0, beta=np.inf, mixing=1.0, vtol=1e-6, max_iter=1000,
                               vthresh=1e-10, verbose=True, ref=True):
-    """Iterates V -> sqrt(z_qp) t until |dV| < vtol; returns the converged SIAM
-    (reference: twosite.py:103-172)."""
+    """Two-site DMFT of the half-filled Hubbard model on the Bethe lattice: the hybridisation of the
+    two-site SIAM is iterated, V -> sqrt(Z) t, until it moves by less than ``vtol`` (or vanishes, or the
+    quasiparticle weight does, or ``max_iter`` is hit); returns the converged SIAM.  Same stopping rules,
+    order of checks and messages as the reference loop (twosite.py:103-172)."""
     siam = SingleImpurityAndersonModel(u, v=[t], mu=u / 2, temp=1 / beta)
-    v = siam.v[0] + 0.1  # must differ from the current value, or the first error is zero
-    m2 = t ** 2
-    it = 0
     stats = IterationStats("Δv")
-    while True:
-        siam.update_hybridization(v)
-        sigma = self_energy(impurity_gf0(z, siam), compute_impurity_gf(z, siam, ref=ref))
-        qp_weight = quasiparticle_weight(z.real, sigma, thresh=vthresh)
-        v_new = mix_values(v, np.sqrt(qp_weight * m2), mixing=mixing)
-        delta_v = np.linalg.norm(v - v_new)
-        stats.append(delta_v)
-        v = v_new
-        if v == 0:
+    v = siam.v[0] + 0.1   # start away from the model's own value: the first step must register a change
+    for it in range(max_iter + 1):
+        v_old = v
+        v, weight = _next_hybridization(z, siam, v_old, t, mixing, vthresh, ref)
+        change = np.linalg.norm(v_old - v)
+        stats.append(change)
+        if v == 0 or change < vtol:
             stats.set_parameter_converged("Hybridization", v)
             break
-        if delta_v < vtol:
-            stats.set_parameter_converged("Hybridization", v)
+        if weight == 0:
+            stats.set_parameter_converged("Quasiparticle weight", weight)
             break
-        elif qp_weight == 0:
-            stats.set_parameter_converged("Quasiparticle weight", qp_weight)
-            break
-        elif it >= max_iter:
+        if it >= max_iter:
             stats.set_maxiter_status(max_iter)
-            break
-        it += 1
     siam.update_hybridization(v)
     if verbose:
-        print("-" * 50)
-        print(f"U:          {u:.2f}")
-        print(stats)
+        print("-" * 50 + f"\nU:          {u:.2f}\n{stats}")
     return siam
 
 
