@@ -340,6 +340,24 @@ def test_hv_more_than_32_bonds_tiny_dn_sectors(cm):
                 assert relerr(y, ref) < HV_RTOL, (nu, nd, variant)
 
 
+def test_hubbard_hamiltonian_csr_helper(cm, golden):
+    """`hubbard_hamiltonian` (BASELINE.md section 3 baseline B, cmpy/models/hubbard.py:25-34): the CSR matrix
+    of a sector from the projector streams == the dense Hamiltonian of the model == the oracle's triplets."""
+    from cmpy_b200.models import HubbardModel
+    from cmpy_b200.models.hubbard import hubbard_hamiltonian
+
+    L = 6
+    nb = chain(L, True)
+    model = HubbardModel(L, nb, inter=4.0, mu=2.0, hop=1.0)
+    sec = model.basis.get_sector(3, 2)
+    a = hubbard_hamiltonian(sec, nb, inter=4.0, eps=-2.0, hop=1.0)
+    n = len(sec.up_states) * len(sec.dn_states)
+    assert a.shape == (n, n)
+    assert_allclose(a.toarray(), model.hamiltonian(sector=sec), atol=1e-13)
+    r, c, v = orc.hubbard_triplets(np.asarray(sec.up_states), np.asarray(sec.dn_states), L, nb, 4.0, -2.0, 1.0)
+    assert_allclose(a.toarray(), orc.coo_dense(n, r, c, v), atol=1e-13)
+
+
 def test_hv_siam_vs_oracle(cm):
     from cmpy_b200.models import SingleImpurityAndersonModel
 
