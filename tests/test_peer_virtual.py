@@ -22,7 +22,9 @@ def _bounds(n, world):
     return [(n * k) // world for k in range(world + 1)]
 
 
-@pytest.mark.parametrize("world,nu,nd", [(2, 70, 131), (3, 70, 131), (5, 33, 64), (8, 257, 40)])
+@pytest.mark.parametrize("world,nu,nd", [(2, 70, 131), (3, 70, 131), (5, 33, 64), (8, 257, 40),
+                                         # odd slab starts, several row tiles, the 4x4 row count
+                                         (4, 1198, 97), (7, 1000, 33), (8, 12870, 45)])
 def test_push_and_pull_definitions(world, nu, nd):
     import torch
     from cmpy_b200 import _lib
