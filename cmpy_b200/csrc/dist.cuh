@@ -164,8 +164,6 @@ struct cmpy_dist_s {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int push_sms = 32;
-  int pull_rows = 64;             // rows per tile of the pull transpose (remote runs of 8 * pull_rows bytes);
-                                  // measured on 2 x B200, 4x4 sector: 32 rows 2.72 ms per H.v, 64: 2.61, 128: 2.65
   ~cmpy_dist_s() {
     cudaFree(d_epoch); cudaFree(d_part); cudaFree(d_coef); cudaFree(d_sum);
     if (side) cudaStreamDestroy(side);
@@ -222,19 +220,11 @@ struct cmpy_dist_s {
     if (rc) return rc;
     if (nr > 0 && num_dn > 0) {
       const double* sc = scaled ? d_coef : nullptr;
-      if (pull_rows == 64) {
-        const i64 ntiles = ((nr + 63) / 64) * ((num_dn + 31) / 32);
-        const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-        peer_transpose_kernel<true, 64><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
-      } else if (pull_rows == 128) {
-        const i64 ntiles = ((nr + 127) / 128) * ((num_dn + 31) / 32);
-        const int g = (int)(ntiles < 148 * 6 ? ntiles : 148 * 6);
-        peer_transpose_kernel<true, 128><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
-      } else {
-        const i64 ntiles = ((nr + 31) / 32) * ((num_dn + 31) / 32);
-        const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-        peer_transpose_kernel<true, 32><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
-      }
+      // 64-row tiles (remote runs of 512 bytes): measured on 2 x B200, 4x4 sector, 32 rows 2.72 ms per H.v,
+      // 64: 2.61, 128: 2.65 (profiles/r2_dist_check_n2_pull*.log)
+      const i64 ntiles = ((nr + 63) / 64) * ((num_dn + 31) / 32);
+      const int g = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+      peer_transpose_kernel<true, 64><<<g, 256, 0, st>>>(y, nr, num_dn, r0, num_up, yt, sc);
       KERNEL_CHECK();
     }
     return CMPY_OK;
@@ -282,8 +272,6 @@ static int dist_create_impl(cmpy_op_s* op_main, cmpy_op_s* op_t, int world, int 
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete d; return cmpy_fail(CMPY_ERR_CUDA, std::string("dist_create: ") + cudaGetErrorString(e)); }
-  if (const char* s = getenv("CMPY_PUSH_SMS")) d->push_sms = atoi(s);
-  if (const char* s = getenv("CMPY_PULL_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 128) d->pull_rows = v; }
   *out = d;
   return CMPY_OK;
 }

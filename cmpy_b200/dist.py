@@ -204,7 +204,7 @@ class ShardedHubbardOperator:
         # one CTA and all shared memory per SM, so without this the two kernels serialise)
         import os
         self._sm_count = torch.cuda.get_device_properties(_lib.device()).multi_processor_count
-        self._push_sms = int(os.environ.get("CMPY_PUSH_SMS", "32"))
+        self._push_sms = 32   # measured on 2 x B200
         # the same choreography as ONE C call (cmpy_hv_apply_sharded): control block in symmetric memory
         # for the library's own barrier / all-reduce kernels
         self._cdist = None
