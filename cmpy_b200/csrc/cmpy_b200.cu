@@ -248,6 +248,7 @@ static LzCtx no_lz() {
 }
 
 API int cmpy_hv_apply(cmpy_op_t op, const double* d_x, double* d_y, void* stream) {
+  NvtxRange nvtx_("cmpy_hv_apply");
   ARG_CHECK(op && d_x && d_y, "null argument");
   ARG_CHECK(d_x != d_y, "hv_apply: x and y must be distinct buffers");
   return op->apply(d_x, d_y, no_lz(), as_stream(stream));
@@ -255,6 +256,7 @@ API int cmpy_hv_apply(cmpy_op_t op, const double* d_x, double* d_y, void* stream
 
 API int cmpy_hubbard_apply_rows(cmpy_op_t op, const double* d_x_slab, double* d_y_slab,
                                 int64_t row0, int64_t nrows, int accumulate, void* stream) {
+  NvtxRange nvtx_("cmpy_hubbard_apply_rows");
   ARG_CHECK(op && d_x_slab && d_y_slab, "null argument");
   HubbardOp* h = dynamic_cast<HubbardOp*>(op);
   ARG_CHECK(h, "apply_rows: not a Hubbard operator");
@@ -313,6 +315,7 @@ API int cmpy_ladder_apply(const int64_t* d_up, int64_t num_up, const int64_t* d_
                           const int64_t* d_up_t, int64_t num_up_t, const int64_t* d_dn_t,
                           int64_t num_dn_t, int pos, int sigma, int dagger, int signed_mode,
                           int ncomp, const double* d_x, double* d_y, void* stream) {
+  NvtxRange nvtx_("cmpy_ladder_apply");
   ARG_CHECK(d_up && d_dn && d_up_t && d_dn_t && d_x && d_y, "null argument");
   ARG_CHECK(sigma == 1 || sigma == 2, "sigma must be UP=1 or DN=2");
   ARG_CHECK(pos >= 0 && pos < 63, "bad site");
@@ -344,6 +347,7 @@ API int cmpy_lanczos_run(cmpy_op_t op, const double* d_v0, double* d_w0, double*
                          double tol, double resid_tol, int check_every, int use_graph,
                          double* h_alpha, double* h_beta, int* h_nit, double* h_e0,
                          double* h_resid, double* d_eigvec, void* stream) {
+  NvtxRange nvtx_("cmpy_lanczos_run");
   return lanczos_run_impl(op, d_v0, d_w0, d_w1, maxit, tol, resid_tol, check_every, use_graph,
                           h_alpha, h_beta, h_nit, h_e0, h_resid, d_eigvec, as_stream(stream));
 }
@@ -362,6 +366,7 @@ API int cmpy_tridiag_lowest(const double* h_alpha, const double* h_beta, int n, 
 API int cmpy_cf_eval(const double* h_alpha, const double* h_beta, int n, double norm2, double e0,
                      int s, const double* d_z, int64_t nz, double* d_g, int accumulate,
                      void* stream) {
+  NvtxRange nvtx_("cmpy_cf_eval");
   ARG_CHECK(h_alpha && n >= 1 && d_z && d_g && nz >= 0, "bad argument");
   ARG_CHECK(n == 1 || h_beta, "null beta");
   ARG_CHECK(s == 1 || s == -1, "s must be +1 or -1");
@@ -444,6 +449,7 @@ API int cmpy_transpose_push(const double* d_x_slab, int64_t nrows, int64_t num_d
 API int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                                    int64_t ld_t, int world, const int64_t* h_col_bounds,
                                    void* const* h_peer_ptrs, int max_ctas, void* stream) {
+  NvtxRange nvtx_("cmpy_transpose_push");
   ARG_CHECK(max_ctas >= 0, "bad argument");
   ARG_CHECK(d_x_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
   PeerTable pt;
@@ -463,6 +469,7 @@ API int cmpy_transpose_push_capped(const double* d_x_slab, int64_t nrows, int64_
 API int cmpy_transpose_pull_acc(double* d_y_slab, int64_t nrows, int64_t num_dn, int64_t row0,
                                 int64_t ld_t, int world, const int64_t* h_col_bounds,
                                 void* const* h_peer_ptrs, void* stream) {
+  NvtxRange nvtx_("cmpy_transpose_pull_acc");
   ARG_CHECK(d_y_slab && nrows >= 0 && num_dn >= 0 && row0 >= 0 && ld_t >= row0 + nrows, "bad argument");
   PeerTable pt;
   int rc = fill_peer_table(pt, world, h_col_bounds, h_peer_ptrs);
@@ -491,6 +498,7 @@ API int cmpy_dist_destroy(cmpy_dist_t d) {
 
 API int cmpy_hv_apply_sharded(cmpy_dist_t d, const double* d_x_slab, double* d_y_slab, int accumulate,
                               void* stream) {
+  NvtxRange nvtx_("cmpy_hv_apply_sharded");
   ARG_CHECK(d && d_x_slab && d_y_slab, "null argument");
   return d->apply(d_x_slab, d_y_slab, accumulate ? 1 : 0, false, as_stream(stream));
 }
@@ -509,6 +517,7 @@ API int cmpy_dist_barrier(cmpy_dist_t d, void* stream) {
 API int cmpy_lanczos_sharded(cmpy_dist_t d, double* d_r_slab, double* d_w_slab, int maxit, double tol,
                              int check_every, double* h_alpha, double* h_beta, int* h_nit, double* h_e0,
                              void* stream) {
+  NvtxRange nvtx_("cmpy_lanczos_sharded");
   return dist_lanczos_impl(d, d_r_slab, d_w_slab, maxit, tol, check_every, h_alpha, h_beta, h_nit, h_e0,
                            as_stream(stream));
 }

@@ -32,6 +32,16 @@ static inline int cmpy_fail(int code, const std::string& msg) {
     }                                                                                    \
   } while (0)
 
+// NVTX range around an ABI call / a phase (visible to ncu --nvtx and Nsight Systems; a function-pointer test
+// when no tool is attached).  The reference has no tracing at all.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 #define KERNEL_CHECK()                                   \
   do {                                                   \
     g_cmpy_launches.fetch_add(1);                        \

@@ -191,6 +191,8 @@ struct cmpy_dist_s {
     // capped to what fits the SMs left free (6 CTAs each).  Measured on 2 x B200, 4x4 sector: 2.86 ms per
     // H.v against 2.96 ms with the push enqueued first (its 8 persistent CTAs per SM then occupy every SM
     // before the dn pass arrives).
+    nvtxRangePushA("sharded H.v: dn pass || push");
+    struct PopAll { int n = 1; ~PopAll() { while (n-- > 0) nvtxRangePop(); } } nvtx_pop;   // early returns pop too
     const bool reserve = world > 1 && push_sms > 0 && push_sms < op_main->sm_count;
     LzCtx nolz; nolz.enabled = 0; nolz.iter = nullptr; nolz.beta = nullptr; nolz.alpha = nullptr;
     nolz.partials = nullptr; nolz.ticket = nullptr;
@@ -212,12 +214,14 @@ struct cmpy_dist_s {
     CU_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
     rc = barrier(st);       // all pushes have landed
     if (rc) return rc;
+    nvtxRangePop(); nvtxRangePushA("sharded H.v: up pass");
     if (nc > 0) {
       rc = op_t->apply_slab(my_xt(), my_yt(), c0, nc, 0, 0, nolz, st);   // up hops, row-local in the dn-major slab
       if (rc) return rc;
     }
     rc = barrier(st);       // every YT slab is complete
     if (rc) return rc;
+    nvtxRangePop(); nvtxRangePushA("sharded H.v: pull-accumulate");
     if (nr > 0 && num_dn > 0) {
       const double* sc = scaled ? d_coef : nullptr;
       // 64-row tiles (remote runs of 512 bytes): measured on 2 x B200, 4x4 sector, 32 rows 2.72 ms per H.v,
