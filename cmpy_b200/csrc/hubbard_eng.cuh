@@ -1,5 +1,5 @@
-// hubbard_eng.cuh -- K4, generation 3: the class-major row engine with warp-uniform hop lists in the
-// CONSTANT bank (uniform datapath) -- Hubbard H.v for uniform hop / U / eps, rows of <= 16 sites.
+// hubbard_eng.cuh -- K4, generation 3: the class-major row engine with warp-uniform hop lists walked from
+// SHARED memory -- Hubbard H.v for uniform hop / U / eps, rows of <= 16 sites.
 //
 // Same matrix elements as hubbard.cuh (ref: cmpy/operators.py:305-527, cmpy/models/hubbard.py:13-22)
 // and the same class-major view of a row as hubbard_cls.cuh: a dn string is (dh, dl), dl = low m bits,
@@ -7,12 +7,14 @@
 // stored in shared memory with an ODD pitch P_k >= S_k (lanes along jj: odd stride, lanes along r:
 // contiguous -- both conflict-free).  What is new:
 //
-//   * every table a warp walks (hop lists, per-column / per-segment descriptors, task lists) lives in
-//     the kernel-parameter constant bank (`__grid_constant__`, <= 32 KB).  The warp index is made
-//     warp-uniform with one SHFL, so ptxas keeps the whole list traversal on the uniform datapath:
-//     one `LDCU.U16 URx, c[0x0][URy+..]` per list entry and `LDS.64 R, [Rlane + URx (+ imm)]` per
-//     32 hop terms -- no address arithmetic, no table look-up through the LSU, no list decode in the
-//     vector pipes.  Inner loops: 1 + 2T instructions per list entry and T blocks of 32 lanes.
+//   * every table a warp walks (hop lists, per-column / per-segment descriptors, task lists) is one compact
+//     struct (EngConst, 8 KB: one byte per list entry) that travels as a `__grid_constant__` kernel parameter
+//     and is copied to shared memory once per CTA (TAB_SMEM).  The warp index is made warp-uniform with one
+//     SHFL, so the list traversal is warp-uniform: one broadcast `LDS` per list entry and
+//     `LDS.64 R, [Rlane + offset (+ imm)]` per 32 hop terms.  The first version walked the lists straight from
+//     the constant bank (`LDCU.U16 UR, c[0x0][UR+..]` on the uniform datapath): fastest on chains, but the 4x4
+//     lattice's 18 KB of tables overran the ~5 KB constant cache of an SM and saturated the GPC-level constant
+//     cache -- hence the compact tables in shared memory.
 //   * phase A (lanes along jj): LL hops + LH hops + diagonal -> ys (in units of hop);
 //     phase B (lanes along r):  HH hops + ys -> y, stored STRAIGHT to global memory: a segment is
 //     contiguous in the row, so the store is coalesced.  There is no third "flat" phase, no
