@@ -367,15 +367,51 @@ class _DeviceOperatorMixin:
             return (re + 1j * im).astype(np.result_type(flat.dtype, np.complex128)).reshape(shape)
         # what scipy (eigsh, expm_multiply) hands over: a pageable numpy vector
         host = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64))
-        res = torch.empty(host.numel(), dtype=torch.float64)
-        pin_in, pin_out = self._host_staging(host.numel())
-        pin_in.copy_(host)
-        dev = pin_in.to(device=_lib.device(), non_blocking=True)
-        y = self.apply(dev)
-        pin_out.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        res.copy_(pin_out)
-        return res.numpy().reshape(shape)
+        # fresh result from numpy's allocator (large arrays are madvise(HUGEPAGE)d: far fewer first-touch faults
+        # than torch.empty -- measured 128 vs 229 ms for the copy into a fresh 1.3 GB array)
+        res_np = np.empty(host.numel(), dtype=np.float64)
+        self._pageable_roundtrip(host, torch.from_numpy(res_np))
+        return res_np.reshape(shape)
+
+    def _pageable_roundtrip(self, host, res, chunks=8):
+        """``res = H host`` for pageable host vectors, in ``chunks`` pieces through the pinned staging buffers:
+        the host copy of piece k+1 into the pinned input overlaps the H2D copy of piece k, and the copy of result
+        piece k out of the pinned buffer overlaps the D2H copy of piece k+1 (the host copies, not PCIe, are the
+        longer leg).  One H.v on the whole vector in between."""
+        torch = _lib.require_cuda()
+        n = host.numel()
+        pin_in, pin_out = self._host_staging(n)
+        dev = getattr(self, "_dev_io", None)
+        if dev is None or dev[0].numel() != n:
+            dev = (torch.empty(n, dtype=torch.float64, device=_lib.device()),
+                   torch.empty(n, dtype=torch.float64, device=_lib.device()))
+            self._dev_io = dev
+        dx, dy = dev
+        cur = torch.cuda.current_stream()
+        side = getattr(self, "_io_stream", None)
+        if side is None:
+            side = self._io_stream = torch.cuda.Stream()
+        chunks = max(1, min(int(chunks), n // (1 << 20) or 1))
+        bounds = [(n * k) // chunks for k in range(chunks + 1)]
+        side.wait_stream(cur)               # dx / dy are free (earlier calls on the current stream are done with them)
+        with torch.cuda.stream(side):
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                pin_in[a:b].copy_(host[a:b])                    # host copy (blocking), then the asynchronous H2D
+                dx[a:b].copy_(pin_in[a:b], non_blocking=True)
+        cur.wait_stream(side)
+        self.apply(dx, out=dy)
+        side.wait_stream(cur)
+        events = []
+        with torch.cuda.stream(side):
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                pin_out[a:b].copy_(dy[a:b], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(side)
+                events.append(ev)
+        for ev, a, b in zip(events, bounds[:-1], bounds[1:]):
+            ev.synchronize()
+            res[a:b].copy_(pin_out[a:b])
+        cur.wait_stream(side)
+        return res
 
     def matvec(self, x, out=None):
         torch = _lib.torch_mod()

@@ -882,6 +882,31 @@ def test_host_tensor_matvec(cm):
     assert float((y - h.matvec(x.cuda()).cpu()).abs().max()) == 0.0
 
 
+def test_numpy_matvec_chunked_roundtrip(cm):
+    """The call scipy makes -- matvec(np.ndarray) -- on a vector long enough for the chunk-pipelined host
+    round trip (8 pieces): same bits as the device call, fresh results, repeated calls, ragged views."""
+    import torch
+    from cmpy_b200.models import HubbardModel
+
+    h = HubbardModel(14, chain(14), inter=4.0, mu=2.0, hop=1.0).hamilton_operator(7, 7)
+    n = h.shape[0]
+    assert n == 3432 * 3432
+    rng = np.random.default_rng(2)
+    work = rng.standard_normal(3 * n + 5)
+    x = work[3:3 + n]                       # a view into a larger work array, like ARPACK's workd
+    ref = h.apply(torch.from_numpy(np.ascontiguousarray(x)).cuda()).cpu().numpy()
+    y1 = h.matvec(x)
+    assert isinstance(y1, np.ndarray) and y1.shape == (n,) and np.array_equal(y1, ref)
+    y2 = h.matvec(2.0 * x)
+    assert np.array_equal(y1, ref) and y2 is not y1      # the first result was not overwritten
+    assert np.array_equal(y2, 2.0 * ref)
+    y3 = h.matvec(x.reshape(n, 1))
+    assert y3.shape == (n, 1) and np.array_equal(y3[:, 0], ref)
+    ys = h.matvec(work[5:5 + 2 * n:2])      # strided view
+    rs = h.apply(torch.from_numpy(np.ascontiguousarray(work[5:5 + 2 * n:2])).cuda()).cpu().numpy()
+    assert np.array_equal(ys, rs)
+
+
 # ---------------------------------------------------------------------------------------
 # f-2: real-time Green's functions (SURVEY 8(f)) against the unmodified reference
 # (tests/golden/reference_tevo.npz, generated by oracle/make_golden_tevo.py)
