@@ -60,15 +60,21 @@ struct EngConst {
   uint32_t task_a[ENG_MAX_TASKS];     // k | blk << 4 | T << 6 | r0 << 8 | nr << 16     (jj0 = 64 * blk)
   uint32_t task_b[ENG_MAX_TASKS];     // k | T << 6 | jj0 << 8 | njj << 16
   uint32_t task_s[ENG_MAX_TASKS];     // staging: k | T << 6 | jj0 << 8 | njj << 16
-  uint16_t ll_start[ENG_MAX_Q];       // per (k, r): first entry of its list ('+' entries, then '-' entries)
-  uint16_t hh_start[ENG_MAX_SEG];     // per class-major segment: the same
-  uint8_t ll_cnt[ENG_MAX_Q];          // (# '+') | (# '-') << 4
-  uint8_t hh_cnt[ENG_MAX_SEG];
+  // One 16-byte descriptor per column (k, r) / per class-major segment, fetched with ONE broadcast LDS.128
+  // (the walk used to cost 2 + 1 + NLH byte loads per column plus one per list entry: 13 of the ~58 shared-memory
+  // wavefronts of a two-block column on the 4x4 lattice):
+  //   cdesc[q]: x = LH source ranks r' of bonds 0..3 (one byte each: rank of dl ^ bit in the source class),
+  //             y = first entry of the LL list in ll_ent | (# '+') << 16 | (# '-') << 20 | lh flags << 24
+  //                 (flag bit b = value of the dl bit of LH bond b, bit 4 + b = parity of its dl part),
+  //             z = the first four '+' entries r' (bytes), w = the first four '-' entries
+  //   sdesc[s]: x = first entry of the HH list in hh_ent | (# '+') << 16 | (# '-') << 20,
+  //             y = offset of the segment in the row, z / w = the first four '+' / '-' entries jj'
+  // Lists of more than four entries of one sign are walked from ll_ent / hh_ent ('+' entries, then '-' entries).
+  uint4 cdesc[ENG_MAX_Q];
+  uint4 sdesc[ENG_MAX_SEG];
   uint8_t ll_ent[ENG_MAX_ENT];        // r'
   uint8_t hh_ent[ENG_MAX_ENT];        // jj'
-  uint8_t lh_off[ENG_MAX_LH][ENG_MAX_Q];  // per (bond, (k, r)): r' (rank of dl ^ bit in the source class)
-  uint8_t lh_flg[ENG_MAX_Q];          // bit b = value of the dl bit of LH bond b; bit 4 + b = parity of its dl part
-  uint16_t goff_cm[ENG_MAX_SEG];      // class-major segment -> offset in the row
+  uint16_t goff_cm[ENG_MAX_SEG];      // class-major segment -> offset in the row (staging)
 };
 
 // ---- per-lane tables (global memory, read once per task / per row) --------------------------------
@@ -146,20 +152,43 @@ ENG_HD void eng_list(const EngConst& C, int i, int n, eng_addr scale, const eng_
   }
 }
 
+// the same for a list of at most four entries packed into one word of the column / segment descriptor
+template <int T, int N, bool NEG, bool HH>
+ENG_HD void eng_acc_pk(uint32_t w, eng_addr scale, const eng_addr* base, double* acc) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const eng_addr e = (eng_addr)((w >> (8 * j)) & 255u) * (HH ? scale : (eng_addr)8u);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const double v = eng_ld(HH ? base[0] + e + 256u * t : base[t] + e);
+      if (NEG) acc[t] -= v; else acc[t] += v;
+    }
+  }
+}
+template <int T, bool NEG, bool HH>
+ENG_HD void eng_list_pk(uint32_t w, int n, eng_addr scale, const eng_addr* base, double* acc) {
+  switch (n) {
+    case 0: break;
+    case 1: eng_acc_pk<T, 1, NEG, HH>(w, scale, base, acc); break;
+    case 2: eng_acc_pk<T, 2, NEG, HH>(w, scale, base, acc); break;
+    case 3: eng_acc_pk<T, 3, NEG, HH>(w, scale, base, acc); break;
+    default: eng_acc_pk<T, 4, NEG, HH>(w, scale, base, acc);
+  }
+}
+
 // LH hops of one column: bond b reads the per-lane source a1 (dl bit set: the lane's dh bit must be clear)
 // or a0 (dl bit clear); lanes whose dh bit does not fit read the zero region
 template <int T, int NLH>
-ENG_HD void eng_lh(const EngConst& C, int q, const eng_addr (*a0)[T], const eng_addr (*a1)[T],
+ENG_HD void eng_lh(uint32_t offs, uint32_t flg, const eng_addr (*a0)[T], const eng_addr (*a1)[T],
                    const uint32_t (*sg)[T], double* acc) {
   // NLH is a compile-time bound (1, 2 or 4 >= the number of LH bonds; the tables of the missing bonds
   // point at the zero region): a branch per bond would cut the column into basic blocks and ptxas
   // then serialises LDS -> LOP3 -> DADD of every bond on one register pair (measured: short-scoreboard
   // stalls 14.9 per issued instruction, 3.6 ms instead of 2.0 ms on the 4x4 sector)
-  const uint32_t flg = C.lh_flg[q];
   double v[NLH][T];
 #pragma unroll
   for (int b = 0; b < NLH; ++b) {
-    const eng_addr off = (eng_addr)C.lh_off[b][q] * 8u;
+    const eng_addr off = (eng_addr)((offs >> (8 * b)) & 255u) * 8u;
     const bool set = ((flg >> b) & 1u) != 0u;
 #pragma unroll
     for (int t = 0; t < T; ++t) v[b][t] = eng_ld((set ? a1[b][t] : a0[b][t]) + off);
@@ -216,15 +245,20 @@ ENG_HD void eng_task_a(const EngConst& C, const EngLane& ln, uint32_t task, eng_
     const int q = q0 + r;
     // (list pointer and counts re-read per column: a pointer carried from column to column ends up in
     //  a vector register and drags the whole list walk off the uniform datapath)
-    const int i = (int)C.ll_start[q];
-    const uint32_t d = C.ll_cnt[q];
-    const int np = (int)(d & 15u), nn = (int)(d >> 4);
+    const uint4 cd = C.cdesc[q];
+    const int np = (int)((cd.y >> 16) & 15u), nn = (int)((cd.y >> 20) & 15u);
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    eng_list<T, false, false>(C, i, np, 8u, xa, acc);
-    eng_list<T, true, false>(C, i + np, nn, 8u, xa, acc);
-    eng_lh<T, NLH>(C, q, a0, a1, sg, acc);
+    if (np <= 4 && nn <= 4) {
+      eng_list_pk<T, false, false>(cd.z, np, 8u, xa, acc);
+      eng_list_pk<T, true, false>(cd.w, nn, 8u, xa, acc);
+    } else {
+      const int i = (int)(cd.y & 0xffffu);
+      eng_list<T, false, false>(C, i, np, 8u, xa, acc);
+      eng_list<T, true, false>(C, i + np, nn, 8u, xa, acc);
+    }
+    eng_lh<T, NLH>(cd.x, cd.y >> 24, a0, a1, sg, acc);
     const double dgl = eng_ld(dg_a + (eng_addr)q * 8u);
     const eng_addr r8 = (eng_addr)r * 8u;
 #pragma unroll
@@ -286,9 +320,8 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
 #pragma unroll 1
   for (int jj = jj0; jj < jj0 + njj; ++jj) {
     const int sgi = sgb + jj;
-    const int i = (int)C.hh_start[sgi];
-    const uint32_t d = C.hh_cnt[sgi];
-    const int goff = (int)C.goff_cm[sgi];
+    const uint4 sd = C.sdesc[sgi];
+    const int goff = (int)sd.y;
     double up[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) up[t] = 0.0;
@@ -300,12 +333,18 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
         for (int t = 0; t < T; ++t)
           g0[q][t] = (q < E.cu && live[t]) ? eng_ldg(xrl + E.up_off[q] + goff + 32 * t) : 0.0;
     }
-    const int np = (int)(d & 15u), nn = (int)(d >> 4);
+    const int np = (int)((sd.x >> 16) & 15u), nn = (int)((sd.x >> 20) & 15u);
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    eng_list<T, false, true>(C, i, np, pk8, xl, acc);
-    eng_list<T, true, true>(C, i + np, nn, pk8, xl, acc);
+    if (np <= 4 && nn <= 4) {
+      eng_list_pk<T, false, true>(sd.z, np, pk8, xl, acc);
+      eng_list_pk<T, true, true>(sd.w, nn, pk8, xl, acc);
+    } else {
+      const int i = (int)(sd.x & 0xffffu);
+      eng_list<T, false, true>(C, i, np, pk8, xl, acc);
+      eng_list<T, true, true>(C, i + np, nn, pk8, xl, acc);
+    }
     if (WITH_UP) {
 #pragma unroll
       for (int q = 0; q < ENG_UPB; ++q)
@@ -592,8 +631,10 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
       (parity((u64)dl, s1[b], s2[b]) ? neg : pos).push_back((uint8_t)lo_rank[nl]);
     }
     if (nle + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 15 || neg.size() > 15) return CMPY_OK;
-    ll_start[q] = nle; C.ll_start[q] = (uint16_t)nle;
-    C.ll_cnt[q] = (uint8_t)(pos.size() | (neg.size() << 4));
+    ll_start[q] = nle;
+    C.cdesc[q].y = (uint32_t)nle | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 20);
+    for (size_t e = 0; e < pos.size() && e < 4; ++e) C.cdesc[q].z |= (uint32_t)pos[e] << (8 * e);
+    for (size_t e = 0; e < neg.size() && e < 4; ++e) C.cdesc[q].w |= (uint32_t)neg[e] << (8 * e);
     for (uint8_t v : pos) C.ll_ent[nle++] = v;
     for (uint8_t v : neg) C.ll_ent[nle++] = v;
     n_ll[q] = (int)(pos.size() + neg.size());
@@ -610,8 +651,11 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
       (parity((u64)dh << m, s1[b], s2[b]) ? neg : pos).push_back((uint8_t)hi_jj[nh]);
     }
     if (nhe + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 15 || neg.size() > 15) return CMPY_OK;
-    hh_start[sgi] = nhe; C.hh_start[sgi] = (uint16_t)nhe;
-    C.hh_cnt[sgi] = (uint8_t)(pos.size() | (neg.size() << 4));
+    hh_start[sgi] = nhe;
+    C.sdesc[sgi].x = (uint32_t)nhe | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 20);
+    C.sdesc[sgi].y = (uint32_t)C.goff_cm[sgi];
+    for (size_t e = 0; e < pos.size() && e < 4; ++e) C.sdesc[sgi].z |= (uint32_t)pos[e] << (8 * e);
+    for (size_t e = 0; e < neg.size() && e < 4; ++e) C.sdesc[sgi].w |= (uint32_t)neg[e] << (8 * e);
     for (uint8_t v : pos) C.hh_ent[nhe++] = v;
     for (uint8_t v : neg) C.hh_ent[nhe++] = v;
     n_hh[sgi] = (int)(pos.size() + neg.size());
@@ -639,12 +683,12 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
       const int dl = dl_of_q[q], k = k_of_q[q];
       const int bit_lo = (dl >> a) & 1;
       const int kp = k + (bit_lo ? -1 : 1);   // class of the source segment
-      C.lh_flg[q] = (uint8_t)(C.lh_flg[q] | (bit_lo << qb));
-      C.lh_off[qb][q] = 0;   // source class empty: the lanes point at the zero region
+      C.cdesc[q].y |= (uint32_t)bit_lo << (24 + qb);
+      // (source class empty: rank byte 0, the lanes point at the zero region)
       if (kp >= 0 && kp <= m && C.H[kp] > 0 && C.H[k] > 0) {
         const int nl = dl ^ (1 << a);
-        C.lh_off[qb][q] = (uint8_t)lo_rank[nl];
-        if (parity((u64)dl, a, m)) C.lh_flg[q] = (uint8_t)(C.lh_flg[q] | (16 << qb));   // bits of dl strictly above a
+        C.cdesc[q].x |= (uint32_t)lo_rank[nl] << (8 * qb);
+        if (parity((u64)dl, a, m)) C.cdesc[q].y |= 16u << (24 + qb);   // bits of dl strictly above a
         n_lh[q] += 1;
       }
     }

@@ -71,7 +71,16 @@ CASES = [
     (12, 5, "ladder", 12), (10, 5, "ring", 10), (8, 4, "chain", 8), (8, 1, "ring", 8), (8, 7, "chain", 8),
     (6, 3, "ring", 6), (5, 2, "chain", 5), (4, 2, "sq22", 4), (16, 1, "sq44", 16), (16, 15, "chain", 16),
     (16, 0, "chain", 16), (16, 16, "chain", 16), (11, 4, "ring", 11), (9, 4, "sq33", 9),
+    # dense halves: lists of more than four entries of one sign (the walk beyond the packed descriptor words)
+    (16, 8, "dense", 16), (12, 6, "dense", 12), (14, 5, "dense", 0),
 ]
+
+
+def dense_halves(L):
+    """All pairs inside the low half, all pairs inside the high half, two bonds across."""
+    m = (L + 1) // 2
+    b = [(i, j) for i in range(m) for j in range(i + 1, m)] + [(i, j) for i in range(m, L) for j in range(i + 1, L)]
+    return b + [(m - 1, m), (0, L - 1)]
 
 
 @pytest.mark.parametrize("L,n_dn,lat,width", CASES)
@@ -79,7 +88,8 @@ CASES = [
 def test_engine_row_matches_direct(emu, L, n_dn, lat, width, nwarps):
     bonds = {"chain": lambda: orc.chain_neighbors(L), "ring": lambda: ring(L), "ladder": lambda: ladder(L),
              "sq44": lambda: orc.square_neighbors(4, 4), "sq43": lambda: orc.square_neighbors(4, 3),
-             "sq33": lambda: orc.square_neighbors(3, 3), "sq22": lambda: orc.square_neighbors(2, 2)}[lat]()
+             "sq33": lambda: orc.square_neighbors(3, 3), "sq22": lambda: orc.square_neighbors(2, 2),
+             "dense": lambda: dense_halves(L)}[lat]()
     bonds = sorted({(min(i, j), max(i, j)) for i, j in bonds if i != j})
     s1 = (ctypes.c_int * len(bonds))(*[b[0] for b in bonds])
     s2 = (ctypes.c_int * len(bonds))(*[b[1] for b in bonds])
