@@ -66,10 +66,10 @@ struct EngConst {
   //   cdesc[q]: x = LH source ranks r' of bonds 0..3 (one byte each: rank of dl ^ bit in the source class),
   //             y = first entry of the LL list in ll_ent | (# '+') << 16 | (# '-') << 20 | lh flags << 24
   //                 (flag bit b = value of the dl bit of LH bond b, bit 4 + b = parity of its dl part),
-  //             z = the first four '+' entries r' (bytes), w = the first four '-' entries
+  //             (z, w) = the first eight list entries r' (bytes; '+' entries, then '-' entries)
   //   sdesc[s]: x = first entry of the HH list in hh_ent | (# '+') << 16 | (# '-') << 20,
-  //             y = offset of the segment in the row, z / w = the first four '+' / '-' entries jj'
-  // Lists of more than four entries of one sign are walked from ll_ent / hh_ent ('+' entries, then '-' entries).
+  //             y = offset of the segment in the row, (z, w) = the first eight list entries jj'
+  // Lists of more than eight entries are walked from ll_ent / hh_ent ('+' entries, then '-' entries).
   uint4 cdesc[ENG_MAX_Q];
   uint4 sdesc[ENG_MAX_SEG];
   uint8_t ll_ent[ENG_MAX_ENT];        // r'
@@ -152,12 +152,12 @@ ENG_HD void eng_list(const EngConst& C, int i, int n, eng_addr scale, const eng_
   }
 }
 
-// the same for a list of at most four entries packed into one word of the column / segment descriptor
+// the same for a list whose entries are bytes of the 64-bit word (z, w) of the column / segment descriptor
 template <int T, int N, bool NEG, bool HH>
-ENG_HD void eng_acc_pk(uint32_t w, eng_addr scale, const eng_addr* base, double* acc) {
+ENG_HD void eng_acc_pk(unsigned long long w, eng_addr scale, const eng_addr* base, double* acc) {
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    const eng_addr e = (eng_addr)((w >> (8 * j)) & 255u) * (HH ? scale : (eng_addr)8u);
+    const eng_addr e = (eng_addr)((uint32_t)(w >> (8 * j)) & 255u) * (HH ? scale : (eng_addr)8u);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const double v = eng_ld(HH ? base[0] + e + 256u * t : base[t] + e);
@@ -166,13 +166,16 @@ ENG_HD void eng_acc_pk(uint32_t w, eng_addr scale, const eng_addr* base, double*
   }
 }
 template <int T, bool NEG, bool HH>
-ENG_HD void eng_list_pk(uint32_t w, int n, eng_addr scale, const eng_addr* base, double* acc) {
+ENG_HD void eng_list_pk(unsigned long long w, int n, eng_addr scale, const eng_addr* base, double* acc) {
   switch (n) {
     case 0: break;
     case 1: eng_acc_pk<T, 1, NEG, HH>(w, scale, base, acc); break;
     case 2: eng_acc_pk<T, 2, NEG, HH>(w, scale, base, acc); break;
     case 3: eng_acc_pk<T, 3, NEG, HH>(w, scale, base, acc); break;
-    default: eng_acc_pk<T, 4, NEG, HH>(w, scale, base, acc);
+    default:
+      eng_acc_pk<T, 4, NEG, HH>(w, scale, base, acc);
+#pragma unroll 1
+      for (int j = 4; j < n; ++j) eng_acc_pk<T, 1, NEG, HH>(w >> (8 * j), scale, base, acc);
   }
 }
 
@@ -250,9 +253,10 @@ ENG_HD void eng_task_a(const EngConst& C, const EngLane& ln, uint32_t task, eng_
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    if (np <= 4 && nn <= 4) {
-      eng_list_pk<T, false, false>(cd.z, np, 8u, xa, acc);
-      eng_list_pk<T, true, false>(cd.w, nn, 8u, xa, acc);
+    if (np + nn <= 8) {
+      const unsigned long long ent = (unsigned long long)cd.z | ((unsigned long long)cd.w << 32);
+      eng_list_pk<T, false, false>(ent, np, 8u, xa, acc);
+      eng_list_pk<T, true, false>(ent >> (8 * np), nn, 8u, xa, acc);
     } else {
       const int i = (int)(cd.y & 0xffffu);
       eng_list<T, false, false>(C, i, np, 8u, xa, acc);
@@ -337,9 +341,10 @@ ENG_HD void eng_task_b(const EngConst& C, uint32_t task, eng_addr xs_a, eng_addr
     double acc[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    if (np <= 4 && nn <= 4) {
-      eng_list_pk<T, false, true>(sd.z, np, pk8, xl, acc);
-      eng_list_pk<T, true, true>(sd.w, nn, pk8, xl, acc);
+    if (np + nn <= 8) {
+      const unsigned long long ent = (unsigned long long)sd.z | ((unsigned long long)sd.w << 32);
+      eng_list_pk<T, false, true>(ent, np, pk8, xl, acc);
+      eng_list_pk<T, true, true>(ent >> (8 * np), nn, pk8, xl, acc);
     } else {
       const int i = (int)(sd.x & 0xffffu);
       eng_list<T, false, true>(C, i, np, pk8, xl, acc);
@@ -633,8 +638,11 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
     if (nle + pos.size() + neg.size() > ENG_MAX_ENT || pos.size() > 15 || neg.size() > 15) return CMPY_OK;
     ll_start[q] = nle;
     C.cdesc[q].y = (uint32_t)nle | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 20);
-    for (size_t e = 0; e < pos.size() && e < 4; ++e) C.cdesc[q].z |= (uint32_t)pos[e] << (8 * e);
-    for (size_t e = 0; e < neg.size() && e < 4; ++e) C.cdesc[q].w |= (uint32_t)neg[e] << (8 * e);
+    {
+      std::vector<uint8_t> all(pos);
+      all.insert(all.end(), neg.begin(), neg.end());
+      for (size_t e = 0; e < all.size() && e < 8; ++e) (e < 4 ? C.cdesc[q].z : C.cdesc[q].w) |= (uint32_t)all[e] << (8 * (e & 3));
+    }
     for (uint8_t v : pos) C.ll_ent[nle++] = v;
     for (uint8_t v : neg) C.ll_ent[nle++] = v;
     n_ll[q] = (int)(pos.size() + neg.size());
@@ -654,8 +662,11 @@ static int build_eng_host(EngHost& T, int num_sites, int n_dn, i64 num_dn, int n
     hh_start[sgi] = nhe;
     C.sdesc[sgi].x = (uint32_t)nhe | ((uint32_t)pos.size() << 16) | ((uint32_t)neg.size() << 20);
     C.sdesc[sgi].y = (uint32_t)C.goff_cm[sgi];
-    for (size_t e = 0; e < pos.size() && e < 4; ++e) C.sdesc[sgi].z |= (uint32_t)pos[e] << (8 * e);
-    for (size_t e = 0; e < neg.size() && e < 4; ++e) C.sdesc[sgi].w |= (uint32_t)neg[e] << (8 * e);
+    {
+      std::vector<uint8_t> all(pos);
+      all.insert(all.end(), neg.begin(), neg.end());
+      for (size_t e = 0; e < all.size() && e < 8; ++e) (e < 4 ? C.sdesc[sgi].z : C.sdesc[sgi].w) |= (uint32_t)all[e] << (8 * (e & 3));
+    }
     for (uint8_t v : pos) C.hh_ent[nhe++] = v;
     for (uint8_t v : neg) C.hh_ent[nhe++] = v;
     n_hh[sgi] = (int)(pos.size() + neg.size());
