@@ -58,3 +58,25 @@ def test_c_heisenberg_vs_numpy(N, n_up, periodic, j, jz):
     o = orcc.HeisenbergOracle(N, n_up, nbl, j, jz)
     assert o.size == len(st)
     assert np.abs(o.matvec(x) - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_c_hv_random_graphs():
+    """Random bond lists (any pair i < j, also long-range), random fillings and both sign conventions
+    (width = L and the Anderson width = 0): C oracle == numpy oracle == dense matrix of the triplet oracle."""
+    rng = np.random.default_rng(20260)
+    for trial in range(12):
+        L = int(rng.integers(3, 9))
+        nb = sorted({tuple(sorted(rng.choice(L, size=2, replace=False).tolist())) for _ in range(int(rng.integers(1, 2 * L)))})
+        nb = [(int(i), int(j)) for i, j in nb]
+        nu, nd = int(rng.integers(0, L + 1)), int(rng.integers(0, L + 1))
+        width = L if trial % 3 else 0
+        inter, eps, hop = float(rng.normal()), float(rng.normal()), float(rng.normal())
+        o = orcc.hubbard_oracle(L, nu, nd, nb, inter, eps, hop, width=width)
+        x = rng.standard_normal(o.size)
+        ref = orc.hubbard_matvec_free(o.up, o.dn, nb, inter, eps, hop, x, width=width)
+        scale = max(np.abs(ref).max(), 1e-300)
+        assert np.abs(o.matvec(x) - ref).max() <= 1e-13 * scale, (L, nb, nu, nd, width)
+        if width == L and 0 < o.size <= 2000:      # the reference's own triplet stream (signs up to num_sites)
+            r, c, v = orc.hubbard_triplets(o.up, o.dn, L, nb, inter, eps, hop)
+            y = orc.coo_matvec(o.size, np.asarray(r), np.asarray(c), np.asarray(v, dtype=np.float64), x)
+            assert np.abs(y - ref).max() <= 1e-12 * scale
