@@ -113,3 +113,44 @@ def test_engine_row_matches_direct(emu, L, n_dn, lat, width, nwarps):
         assert np.isfinite(y).all()
         assert np.abs(y - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
         assert info[4] <= 32000   # the constant-bank table must fit the kernel-parameter space
+
+
+def test_engine_random_graphs(emu):
+    """Random bond graphs (dense or sparse inside the halves, at most four bonds across), fillings, sign widths and
+    warp counts: the descriptor tables (packed list entries, LH ranks / flags) against the direct evaluation."""
+    from math import comb
+
+    rng = np.random.default_rng(777)
+    ran = 0
+    for trial in range(40):
+        L = int(rng.integers(6, 17))
+        m = (L + 1) // 2
+        lo = [(i, j) for i in range(m) for j in range(i + 1, m)]
+        hi = [(i, j) for i in range(m, L) for j in range(i + 1, L)]
+        cross = [(i, j) for i in range(m) for j in range(m, L)]
+        pick = lambda pool, k: [pool[t] for t in rng.choice(len(pool), size=min(k, len(pool)), replace=False)] if pool else []
+        bonds = sorted(set(pick(lo, int(rng.integers(0, 12))) + pick(hi, int(rng.integers(0, 12))) + pick(cross, int(rng.integers(0, 5)))))
+        if not bonds:
+            continue
+        n_dn = int(rng.integers(1, L))
+        width = L if trial % 4 else 0
+        nwarps = int(rng.choice([32, 16, 7]))
+        s1 = (ctypes.c_int * len(bonds))(*[b[0] for b in bonds])
+        s2 = (ctypes.c_int * len(bonds))(*[b[1] for b in bonds])
+        nd = comb(L, n_dn)
+        x = rng.standard_normal(nd)
+        ups = int(rng.integers(0, 1 << L))
+        e_up, eps0, u0, hop0 = float(rng.normal()), float(rng.normal()), float(rng.normal()), float(rng.choice([1.0, -0.7, 2.5]))
+        y = np.full(nd, np.nan)
+        info = (ctypes.c_int * 8)()
+        rc = emu.eng_emu_row(L, n_dn, len(bonds), s1, s2, width, eps0, u0, hop0, ups, e_up, nwarps, 0,
+                             x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                             y.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), info)
+        if rc == 1:
+            continue          # outside the engine's range (row too short, list too long ...)
+        assert rc == 0, (rc, L, bonds, n_dn)
+        ref = direct_row(L, n_dn, bonds, width, eps0, u0, hop0, ups, e_up, x)
+        assert np.isfinite(y).all()
+        assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (L, bonds, n_dn, width, nwarps)
+        ran += 1
+    assert ran >= 15, ran
