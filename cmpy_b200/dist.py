@@ -487,6 +487,23 @@ def lanczos_sharded(op, v0_local=None, maxit=500, tol=1e-10, check_every=10, see
         w.div_(b)
         v, w = w, v
     ah, bh = alphas[:nit].cpu().numpy(), betas[:nit].cpu().numpy()
+    # usable length: a Krylov breakdown (invariant subspace) between two checks leaves a beta ~ 0 followed by
+    # meaningless coefficients -- cut there, like cmpy_lanczos_sharded and the single-GPU driver do
+    m_use, scale = nit, 0.0
+    for i in range(nit):
+        if not (np.isfinite(ah[i]) and np.isfinite(bh[i])):
+            m_use = i
+            break
+        scale = max(scale, abs(float(ah[i])) + abs(float(bh[i])))
+        if bh[i] <= 1e-13 * max(scale, 1.0):
+            m_use = i + 1
+            break
+    if m_use < nit:
+        nit = max(m_use, 1)
+        ah, bh = ah[:nit].copy(), bh[:nit].copy()
+        e0 = (float(eigvalsh_tridiagonal(ah, bh[:nit - 1], select="i", select_range=(0, 0))[0])
+              if nit > 1 else float(ah[0]))
+        converged = True
     if not want_vector:
         return e0, ah, bh, nit, converged
     # second pass: psi = sum_j s_j v_j with s the lowest eigenvector of the Lanczos matrix

@@ -147,3 +147,30 @@ def test_shard_plan_host():
     p = ShardPlan(184756, 184756, 8, 0)
     # 29.9 GB out per GPU per transpose at L=20
     assert abs(p.bytes_out_per_hv() / 2 / 1e9 - 29.87) < 0.1
+
+
+def test_lanczos_sharded_truncates_at_breakdown():
+    """Python recurrence with checks only at the end (the call pattern of the sharded continued fraction):
+    more iterations than the sector has dimensions -> the Krylov space breaks down on the way; the returned
+    coefficients stop at the breakdown and the lowest Ritz value is the exact E0."""
+    from cmpy_b200.dist import ShardedHubbardOperator, lanczos_sharded
+
+    L, nu, nd = 4, 2, 2
+    nb = orc.chain_neighbors(L, periodic=True)
+    up, dn = orc.enumerate_states(L, nu), orc.enumerate_states(L, nd)
+    be = OracleBackend(up, dn, nb, 4.0, -2.0, 1.0, L)
+    op = ShardedHubbardOperator(_Model(), nu, nd, backend=be, up_states=up, dn_states=dn)
+    dim = len(up) * len(dn)
+    e0, al, bt, nit, conv = lanczos_sharded(op, maxit=3 * dim, tol=0.0, check_every=3 * dim)
+    r, c, v = orc.hubbard_triplets(up, dn, L, nb, 4.0, -2.0, 1.0)
+    e_ref = np.linalg.eigvalsh(orc.coo_dense(dim, r, c, v))[0]
+    # (in floating point the recurrence restarts from round-off before beta reaches the threshold: no cut is
+    #  required here, only finite coefficients and the right lowest Ritz value)
+    assert 1 <= nit <= 3 * dim and len(al) == nit and len(bt) == nit
+    assert np.isfinite(al).all() and np.isfinite(bt).all()
+    assert abs(e0 - e_ref) < 1e-9
+    # a start vector that IS an eigenvector: breakdown after one step
+    w, vec = np.linalg.eigh(orc.coo_dense(dim, r, c, v))
+    e1, al1, bt1, nit1, conv1 = lanczos_sharded(op, v0_local=torch.from_numpy(vec[:, 3].copy()), maxit=50, tol=0.0,
+                                                check_every=50)
+    assert nit1 == 1 and conv1 and abs(e1 - w[3]) < 1e-10
